@@ -1,0 +1,187 @@
+/* icp_b200.h -- C ABI of the B200-native ICP hot path (libicp_b200.so).
+ *
+ * Drop-in boundary for ONE path of B1AnKAlpha/IterativeClosestPoint: the ICP iteration loop of the
+ * reference's core/ engine (target octree build -> exact nearest neighbour per source point -> 3-sigma
+ * rejection + centroid / cross-covariance -> 3x3 SVD Kabsch solve -> apply).  Plain pointers and sizes
+ * only; no C++/torch types.  Every entry point cites the reference interface it replaces
+ * (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - Point arrays are AoS `double xyz[n][3]`, i.e. exactly `std::vector<Point3D>::data()`
+ *     (PointCloudRegistration/core/pointcloud.h:12-23: struct Point3D { double x, y, z; }).
+ *   - 4x4 transforms are ROW-major double[16] (the reference's Eigen::Matrix4d is column-major; the C++
+ *     adapter in icp_b200_engine.hpp converts).
+ *   - All functions return an icp_status; ICP_OK == 0.  Nothing throws, nothing falls back to the CPU:
+ *     without a usable CUDA device every call fails with ICP_CUDA_ERROR.
+ *   - A handle is bound to one CUDA device and is not re-entrant (the reference engine is not either:
+ *     services/registrationservice.cpp:188-191 guards it with m_isRegistering).
+ */
+#ifndef ICP_B200_H
+#define ICP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICP_B200_ABI_VERSION 1
+
+typedef struct icp_b200_ctx* icp_handle;
+
+/* Status codes map 1:1 to the reference's failure exits. */
+typedef enum icp_status {
+    ICP_OK = 0,
+    ICP_EMPTY_INPUT = 1,      /* core/icpengine.cpp:26-34  finished(false, "点云数据为空" / "源点云或目标点云为空") */
+    ICP_CANCELLED = 2,        /* core/icpengine.cpp:160-164 finished(false, "用户取消")                              */
+    ICP_TOO_FEW_INLIERS = 3,  /* core/icpengine.cpp:319-323 finished(false, "有效点对不足")                          */
+    ICP_INVALID_ARGUMENT = 4,
+    ICP_CUDA_ERROR = 5,
+    ICP_NCCL_ERROR = 6,
+    ICP_NO_OCTREE = 7         /* stage call issued before icp_octree_build */
+} icp_status;
+
+/* The engine (PointCloudRegistration/core/) and the CLI program (icp_registration.cpp) implement the same
+ * loop with the differences tabulated in SURVEY.md 3.3; `variant` selects which one is reproduced. */
+typedef enum icp_variant {
+    ICP_VARIANT_ENGINE = 0,   /* core/icpengine.cpp:117-394 */
+    ICP_VARIANT_CLI = 1       /* icp_registration.cpp:443-622 */
+} icp_variant;
+
+/* struct ICPParameters (core/icpengine.h:13-19) + variant. */
+typedef struct icp_params {
+    int32_t max_iterations;     /* maxIterations   = 50   */
+    int32_t octree_max_points;  /* octreeMaxPoints = 10   */
+    int32_t octree_max_depth;   /* octreeMaxDepth  = 20 ; 1..21 supported (3 bits/level in a 64-bit key) */
+    int32_t variant;            /* icp_variant */
+    double tolerance;           /* tolerance       = 1e-6 */
+    double sigma_multiplier;    /* sigmaMultiplier = 3.0  */
+} icp_params;
+
+/* struct IterationResult (core/icpengine.h:24-32). */
+typedef struct icp_iteration {
+    int32_t iteration;          /* 1-based */
+    int32_t valid_points;
+    int32_t outlier_points;
+    int32_t has_angles;         /* 0 for the convergence record, whose angle fields the reference leaves unset (icpengine.cpp:294-303) */
+    double rmse;
+    double transform[16];       /* cumulative, row-major */
+    double rotation_angle;      /* degrees, acos((tr R - 1)/2) without clamping (icpengine.cpp:361) */
+    double translation_distance;
+} icp_iteration;
+
+/* Per-iteration statistics of stages a9-a11 (core/icpengine.cpp:187-278). */
+typedef struct icp_stats {
+    double min_distance, max_distance;  /* over finite distances */
+    double mean, std_dev, threshold, rmse, sum_sq;
+    int64_t problem_count, valid_count, outlier_count;
+} icp_stats;
+
+/* struct ICPResult (core/icpengine.h:37-44) + what the CLI's ICP() returns through its out-parameters. */
+typedef struct icp_result {
+    int32_t status;             /* icp_status of the run */
+    int32_t success;            /* ICPResult::success */
+    int32_t total_iterations;   /* ICPResult::totalIterations (= history length on the success exits, 0 otherwise) */
+    int32_t loop_iterations;    /* NN passes executed */
+    int32_t history_len;        /* records written to `history` (kept on failure exits too) */
+    int32_t history_cap;        /* in: capacity of `history` */
+    double final_rmse;          /* ICPResult::finalRMSE */
+    double final_R[9];          /* ICPResult::finalR ; CLI variant: the LAST incremental R (icp_registration.cpp:616-621) */
+    double final_t[3];
+    double cumulative_T[16];
+    double last_T[16];
+    icp_iteration* history;     /* in: caller-owned array of history_cap records, may be NULL */
+    /* device-side timing of the run (CUDA events on the handle's stream), milliseconds */
+    float ms_h2d, ms_build, ms_loop, ms_d2h, ms_nn_total, ms_nn_first;
+} icp_result;
+
+typedef struct icp_octree_info {
+    int64_t n_points, n_nodes, n_leaves, node_bytes, point_bytes;
+    int32_t depth, max_points, max_depth, pad_;
+    double root_lo[3], root_hi[3];
+    float build_ms, pad2_;      /* device time of the last icp_octree_build (keys + sort + node table) */
+} icp_octree_info;
+
+/* Callbacks replacing the engine's Qt signals (core/icpengine.h:70-75).  They fire on the calling thread,
+ * once per iteration, in the reference's order: log -> iterationCompleted -> progressUpdated
+ * (icpengine.cpp:364-367). */
+typedef void (*icp_iteration_cb)(const icp_iteration* it, void* user);
+typedef void (*icp_progress_cb)(int iteration, int total, double rmse, void* user);
+typedef void (*icp_log_cb)(const char* utf8_message, void* user);
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+int icp_create(icp_handle* out, int device_id);                 /* ICPEngine::ICPEngine (icpengine.cpp:7-13) */
+void icp_destroy(icp_handle h);                                 /* ICPEngine::~ICPEngine */
+const char* icp_last_error(icp_handle h);                       /* detail for CUDA/NCCL/argument failures */
+int icp_abi_version(void);
+
+int icp_set_params(icp_handle h, const icp_params* p);          /* ICPEngine::setParameters (icpengine.cpp:19-22) */
+int icp_get_params(icp_handle h, icp_params* p);                /* ICPEngine::getParameters (icpengine.h:61) */
+void icp_default_params(icp_params* p);                         /* ICPParameters defaults (icpengine.h:13-19) */
+int icp_set_callbacks(icp_handle h, icp_iteration_cb on_iteration, icp_progress_cb on_progress, icp_log_cb on_log,
+                      void* user);
+/* Tuning knobs that never change results: "nn_mode" (0 = literal root traversal, 1 = seeded, default),
+ * "order_queries" (Morton-order the source internally, default 1), "write_mask" (keep the inlier mask). */
+int icp_set_option(icp_handle h, const char* key, double value);
+
+/* ---- the whole hot path, HOST buffers in and out ------------------------------------------------- */
+/* ICPEngine::registerPointClouds (icpengine.cpp:24-60 -> runICP :117-394) and the CLI's ICP()
+ * (icp_registration.cpp:443-446).  `src_xyz` is updated in place on the exits where the reference writes
+ * the source back (success / divergence / max iterations; CLI also on <3 inliers) and left untouched
+ * otherwise.  `stop_flag` (may be NULL) is polled once per iteration like m_shouldStop (icpengine.cpp:160). */
+int icp_register(icp_handle h, double* src_xyz, int64_t n_src, const double* tgt_xyz, int64_t n_tgt,
+                 icp_result* out, const volatile int* stop_flag);
+
+/* Same loop on inputs that are already resident in this handle's device memory: the target uploaded by
+ * icp_octree_build and the source by icp_source_upload.  Used by bench.py for the device-resident figure
+ * and by the sharded driver.  `src_out_xyz` may be NULL (no write-back copy). */
+int icp_source_upload(icp_handle h, const double* src_xyz, int64_t n_src);
+int icp_register_resident(icp_handle h, int64_t n_src_global, icp_result* out, double* src_out_xyz,
+                          const volatile int* stop_flag);
+
+/* ---- stages, individually callable (parity tests, benchmarks) -------------------------------------- */
+/* Octree::Octree (core/octree.cpp:41-77 -> buildTree :86-126; CLI twin icp_registration.cpp:155-185). */
+int icp_octree_build(icp_handle h, const double* tgt_xyz, int64_t n_tgt, int max_points, int max_depth);
+int icp_octree_get_info(icp_handle h, icp_octree_info* info);
+/* Pre-order dump (children in octant order) for structure parity; same layout as the oracle's dump.
+ * Call with NULL arrays to get the sizes. */
+int icp_octree_dump(icp_handle h, int64_t* n_nodes, int64_t* n_leaf_points, int32_t* depth, uint64_t* key,
+                    uint8_t* is_leaf, int32_t* count, double* box6, int32_t* leaf_idx);
+/* Octree::findNearest for n queries (core/octree.cpp:175-184; loop core/icpengine.cpp:172-184).
+ * idx_out receives indices into the ORIGINAL target order; dist_out (may be NULL) the distances of
+ * computeDistance (icpengine.cpp:68-74).  `kernel_ms` (may be NULL) receives the NN kernel's device time. */
+int icp_nn_query(icp_handle h, const double* q_xyz, int64_t n, int32_t* idx_out, double* dist_out, float* kernel_ms);
+/* Stages a9-a11 on caller-supplied correspondences (core/icpengine.cpp:187-278; CLI :499-541). */
+int icp_iteration_stats(icp_handle h, const double* src_xyz, int64_t n, const int32_t* idx, int iteration,
+                        double* dist_out, uint8_t* inlier_mask_out, icp_stats* stats_out);
+/* ICPEngine::computeBestFitTransform (icpengine.cpp:76-115) / best_fit_transform (icp_registration.cpp:389-440)
+ * on n matched pairs; T_out row-major. */
+int icp_best_fit_transform(icp_handle h, const double* a_xyz, const double* b_xyz, int64_t n, double* T_out);
+/* The single-warp SVD + reflection fix + translation on a caller-supplied H and centroids (icpengine.cpp:93-112). */
+int icp_solve_from_H(icp_handle h, const double* H9, const double* cA3, const double* cB3, double* T_out,
+                     double* U9, double* S3, double* V9);
+/* `src = T * src` (icpengine.cpp:345-346); also PointCloud::applyTransform's consumer path. */
+int icp_apply_transform(icp_handle h, const double* T16, double* xyz, int64_t n);
+
+/* ---- multi-GPU: source sharded by point range, target octree replicated ------------ */
+/* One handle per process/GPU.  `unique_id` is NCCL's 128-byte ncclUniqueId created by rank 0
+ * (icp_comm_unique_id) and distributed by the host plumbing (torch.distributed in this repo). */
+int icp_comm_unique_id(icp_handle h, void* unique_id_128);
+int icp_comm_init(icp_handle h, int rank, int n_ranks, const void* unique_id_128);
+int icp_comm_destroy(icp_handle h);
+/* icp_register on this rank's shard of the source; `n_src_global` is the total source size (the N of
+ * the mean / variance).  All ranks return identical results (rank-ordered summation of the gathered partials). */
+int icp_register_sharded(icp_handle h, double* src_shard_xyz, int64_t n_shard, int64_t n_src_global,
+                         const double* tgt_xyz, int64_t n_tgt, icp_result* out, const volatile int* stop_flag);
+
+/* ---- many small independent registrations (BASELINE.json config #5) ---------------------------------- */
+int icp_register_batch(icp_handle h, int32_t n_pairs, double* const* src_xyz, const int64_t* n_src,
+                       const double* const* tgt_xyz, const int64_t* n_tgt, icp_result* results);
+
+/* Number of kernels this library has launched on the handle since creation (bench.py's gpu_launches). */
+int64_t icp_kernel_launches(icp_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICP_B200_H */

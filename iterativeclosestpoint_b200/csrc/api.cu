@@ -1,0 +1,842 @@
+// C ABI of libicp_b200.so (include/icp_b200.h): context, host orchestration of the iteration loop
+// (replaces ICPEngine::registerPointClouds / runICP, core/icpengine.cpp:24-60,117-394, and the CLI's ICP(),
+// icp_registration.cpp:443-622) and the sharded multi-GPU driver.
+#include "internal.h"
+#include <nccl.h>
+#include <dlfcn.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <new>
+
+namespace icpb {
+
+// iter.cu / build.cu entry points not in internal.h
+int stage_a_finish(Ctx* c, const StatA* part, int n_part, StatA* rank_part_slot, const StatA* all_rank_parts, int n_ranks,
+                   int iter, bool finalize);
+int stage_a_finalize(Ctx* c, const StatA* all_rank_parts, int n_ranks, int iter);
+int dist_from_idx_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const int32_t* idx, int64_t n,
+                         uint32_t* pos_out, double* dist_out, StatA* part, int* n_part);
+int stage_b_blocks(Ctx* c, int64_t n);
+int stage_b_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const uint32_t* pos, const double* dist,
+                   int64_t n, uint8_t* mask_out, double* part, double* rank_part_slot);
+int pairs_b_launch(Ctx* c, const double* a_xyz, const double* b_xyz, int64_t n, double* part, double* out17);
+int solve_launch(Ctx* c, const double* rank_parts, int n_ranks);
+int bestfit_launch(Ctx* c, const double* b17, const double* a0, const double* b0, double* T_out);
+int solve_from_H_launch(Ctx* c, const double* in15, double* out37);
+int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n);
+int unsort_results_launch(Ctx* c, const uint32_t* pos, const double* dist, const uint32_t* perm, int64_t n, int32_t* idx_out,
+                          double* dist_out);
+int aos_to_soa_launch(Ctx* c, const double* xyz, int64_t n, double* sx, double* sy, double* sz);
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time so that the library shares the process's already-loaded libnccl.so.2
+// (torch's bundled copy when driven from Python) and has no link-time dependency for 1-GPU users.
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi* nccl_load(Ctx* c) {
+    if (c->nccl) return c->nccl;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* nm : names) {
+        lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) {
+        c->err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+        return nullptr;
+    }
+    NcclApi* a = new NcclApi();
+    a->lib = lib;
+    a->GetUniqueId = (decltype(a->GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    a->CommInitRank = (decltype(a->CommInitRank))dlsym(lib, "ncclCommInitRank");
+    a->CommDestroy = (decltype(a->CommDestroy))dlsym(lib, "ncclCommDestroy");
+    a->AllGather = (decltype(a->AllGather))dlsym(lib, "ncclAllGather");
+    a->GetErrorString = (decltype(a->GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!a->GetUniqueId || !a->CommInitRank || !a->CommDestroy || !a->AllGather || !a->GetErrorString) {
+        c->err = "libnccl.so.2 lacks a required symbol";
+        delete a;
+        return nullptr;
+    }
+    c->nccl = a;
+    return a;
+}
+
+#define ICPB_NCCL(ctx, call)                                                                   \
+    do {                                                                                       \
+        ncclResult_t r__ = (call);                                                             \
+        if (r__ != ncclSuccess) {                                                              \
+            (ctx)->err = std::string(#call) + ": " + (ctx)->nccl->GetErrorString(r__);         \
+            return ICP_NCCL_ERROR;                                                             \
+        }                                                                                      \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+static void log_msg(Ctx* c, const char* fmt, ...) {
+    if (!c->on_log) return;
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    c->on_log(buf, c->user);
+}
+
+static int ensure_run_buffers(Ctx* c, int64_t n) {
+    ICPB_TRY(devbuf_reserve(c, c->pos, (size_t)n * sizeof(uint32_t)));
+    ICPB_TRY(devbuf_reserve(c, c->dist, (size_t)n * sizeof(double)));
+    ICPB_TRY(devbuf_reserve(c, c->mask, (size_t)n));
+    const size_t nbA = (size_t)nn_grid_blocks(n) + 1024;
+    ICPB_TRY(devbuf_reserve(c, c->part_a, nbA * sizeof(StatA)));
+    ICPB_TRY(devbuf_reserve(c, c->part_b, (size_t)(stage_b_blocks(c, n) + 8) * STATB_DOUBLES * sizeof(double)));
+    ICPB_TRY(devbuf_reserve(c, c->gather_a, (size_t)std::max(c->n_ranks, 1) * sizeof(StatA) + 64));
+    ICPB_TRY(devbuf_reserve(c, c->gather_b, (size_t)std::max(c->n_ranks, 1) * STATB_DOUBLES * sizeof(double) + 64));
+    return ICP_OK;
+}
+
+static int ensure_source_buffers(Ctx* c, int64_t n) {
+    ICPB_TRY(devbuf_reserve(c, c->sx, (size_t)n * sizeof(double)));
+    ICPB_TRY(devbuf_reserve(c, c->sy, (size_t)n * sizeof(double)));
+    ICPB_TRY(devbuf_reserve(c, c->sz, (size_t)n * sizeof(double)));
+    ICPB_TRY(devbuf_reserve(c, c->sperm, (size_t)n * sizeof(uint32_t)));
+    return ICP_OK;
+}
+
+static void identity16(double* T) {
+    for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+}
+
+// rotationAngle / translationDistance of a cumulative transform (icpengine.cpp:356-362); evaluated on the host
+// with the C library's acos, as the reference does.  Summation orders follow the reference build's Eigen
+// reductions (trace = a0 + (a1 + a2), squared norm likewise).
+static void angles_of(const double* T, double* angle_deg, double* trans) {
+    volatile double tr = T[0] + (T[5] + T[10]);
+    *angle_deg = std::acos((tr - 1.0) / 2.0) * 180.0 / M_PI;
+    volatile double a = T[3] * T[3], b = T[7] * T[7], cc = T[11] * T[11];
+    volatile double s = b + cc;
+    *trans = std::sqrt(a + s);
+}
+
+// Upload a host AoS cloud into `stage` (device) -- pinned staging is left to the caller's allocator; plain
+// cudaMemcpyAsync from pageable memory is what a drop-in caller with a std::vector will hit.
+static int upload(Ctx* c, DevBuf& stage, const double* host_xyz, int64_t n) {
+    ICPB_TRY(devbuf_reserve(c, stage, (size_t)n * 3 * sizeof(double)));
+    ICPB_CUDA(c, cudaMemcpyAsync(stage.p, host_xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return ICP_OK;
+}
+
+static int source_from_device_aos(Ctx* c, const double* d_xyz, int64_t n) {
+    ICPB_TRY(ensure_source_buffers(c, n));
+    c->n_src = n;
+    if (c->opt_order_queries && n > 1)
+        return order_queries(c, d_xyz, n, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p, (uint32_t*)c->sperm.p);
+    c->src_identity_perm = true;
+    return aos_to_soa_launch(c, d_xyz, n, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p);
+}
+
+// The iteration loop on the resident source/target.  n_global = N of the mean/variance.
+static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile int* stop_flag, bool* write_back) {
+    const icp_params& P = c->params;
+    const int64_t n = c->n_src;
+    const int variant = P.variant;
+    ICPB_TRY(ensure_run_buffers(c, std::max<int64_t>(n, 1)));
+
+    LoopState hs;
+    std::memset(&hs, 0, sizeof hs);
+    hs.prev_error = 1e10;  // icpengine.cpp:156
+    hs.no_improve = 0;
+    identity16(hs.T_pending);
+    identity16(hs.T_last);
+    identity16(hs.T_cum);
+    for (int a = 0; a < 3; ++a) hs.pivot_a[a] = hs.pivot_b[a] = 0.5 * (c->tree.root_lo[a] + c->tree.root_hi[a]);
+    hs.tolerance = P.tolerance;
+    hs.sigma = (variant == ICP_VARIANT_CLI) ? 3.0 : P.sigma_multiplier;  // icp_registration.cpp:523
+    hs.variant = variant;
+    hs.max_iterations = P.max_iterations;
+    hs.n_global = n_global;
+    ICPB_CUDA(c, cudaMemcpyAsync(c->d_state, &hs, sizeof hs, cudaMemcpyHostToDevice, c->stream));
+
+    out->history_len = 0;
+    out->loop_iterations = 0;
+    out->status = ICP_OK;
+    out->ms_nn_total = 0.f;
+    out->ms_nn_first = 0.f;
+    *write_back = true;
+    int n_hist = 0;
+    double last_rmse = 0.0, prev_error = 1e10;
+    double T_last[16], T_cum[16];
+    identity16(T_last);
+    identity16(T_cum);
+
+    StatA* part_a = (StatA*)c->part_a.p + 64;  // first 64 entries are scratch of the build
+    StatA* rank_a = (StatA*)c->gather_a.p;
+    double* rank_b = (double*)c->gather_b.p;
+    double* part_b = (double*)c->part_b.p;
+    const double init_best = (variant == ICP_VARIANT_CLI) ? 1e20 : DBL_MAX;  // octree.cpp:180 vs icp_registration.cpp:201
+
+    ICPB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    for (int iter = 0; iter < P.max_iterations; ++iter) {
+        if (variant == ICP_VARIANT_ENGINE && stop_flag && *stop_flag) {  // icpengine.cpp:160-164
+            log_msg(c, "registration stopped");
+            out->status = ICP_CANCELLED;
+            *write_back = false;
+            break;
+        }
+        log_msg(c, "iteration %d/%d ...", iter + 1, P.max_iterations);
+        out->loop_iterations = iter + 1;
+
+        NNLaunch L;
+        L.sx = (double*)c->sx.p; L.sy = (double*)c->sy.p; L.sz = (double*)c->sz.p;
+        L.ox = (double*)c->sx.p; L.oy = (double*)c->sy.p; L.oz = (double*)c->sz.p;
+        L.n = n;
+        L.pos_out = (uint32_t*)c->pos.p;
+        L.dist_out = (double*)c->dist.p;
+        L.prev_pos = (iter > 0 && c->opt_nn_mode == 1) ? (uint32_t*)c->pos.p : nullptr;
+        L.part_a = part_a;
+        L.state = c->d_state;
+        L.apply_pending = 1;
+        L.mode = c->opt_nn_mode;
+        L.init_best = init_best;
+        ICPB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+        ICPB_TRY(nn_launch(c, L));
+        ICPB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+
+        const int nbA = nn_grid_blocks(n);
+        if (c->n_ranks > 1) {
+            ICPB_TRY(stage_a_finish(c, part_a, nbA, rank_a + c->rank, rank_a, c->n_ranks, iter, false));
+            ICPB_NCCL(c, c->nccl->AllGather(rank_a + c->rank, rank_a, sizeof(StatA) / sizeof(double), ncclFloat64,
+                                            (ncclComm_t)c->comm, c->stream));
+            ICPB_TRY(stage_a_finalize(c, rank_a, c->n_ranks, iter));
+        } else {
+            ICPB_TRY(stage_a_finish(c, part_a, nbA, rank_a, rank_a, 1, iter, true));
+        }
+        ICPB_TRY(stage_b_launch(c, L.sx, L.sy, L.sz, L.pos_out, L.dist_out, n, c->opt_write_mask ? (uint8_t*)c->mask.p : nullptr,
+                                part_b, rank_b + (size_t)c->rank * STATB_DOUBLES));
+        if (c->n_ranks > 1)
+            ICPB_NCCL(c, c->nccl->AllGather(rank_b + (size_t)c->rank * STATB_DOUBLES, rank_b, STATB_DOUBLES, ncclFloat64,
+                                            (ncclComm_t)c->comm, c->stream));
+        ICPB_TRY(solve_launch(c, rank_b, c->n_ranks));
+        ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+        {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+            out->ms_nn_total += ms;
+            if (iter == 0) out->ms_nn_first = ms;
+        }
+        const IterRecord rec = *c->h_rec;
+        if (rec.problems > 0.0) log_msg(c, "warning: %.0f abnormal distance values", rec.problems);
+        log_msg(c, "  distance range: min=%.6f, max=%.6f", rec.dmin, rec.dmax);
+        log_msg(c, "  distance stats: mean=%.6f, std=%.6f, threshold=%.6f", rec.mean, rec.std_dev, rec.threshold);
+        log_msg(c, "  RMSE = %.6f (valid: %d/%lld, outliers removed: %d)", rec.rmse, rec.valid_points, (long long)n_global,
+                rec.outlier_points);
+        std::memcpy(T_cum, rec.T_cum, sizeof T_cum);
+        std::memcpy(T_last, rec.T_last, sizeof T_last);
+        if (rec.exit_code == 0 || rec.exit_code == 3) prev_error = rec.rmse;
+
+        icp_iteration it;
+        std::memset(&it, 0, sizeof it);
+        it.iteration = iter + 1;
+        it.rmse = rec.rmse;
+        it.valid_points = rec.valid_points;
+        it.outlier_points = rec.outlier_points;
+        std::memcpy(it.transform, rec.T_cum, sizeof it.transform);
+
+        if (rec.exit_code == 1) {  // converged: icpengine.cpp:291-305 ; CLI :551-554
+            log_msg(c, "converged at iteration %d", iter + 1);
+            if (variant == ICP_VARIANT_ENGINE) {
+                it.has_angles = 0;
+                if (out->history && n_hist < out->history_cap) out->history[n_hist] = it;
+                ++n_hist;
+                last_rmse = rec.rmse;
+                if (c->on_iteration) c->on_iteration(&it, c->user);
+                if (c->on_progress) c->on_progress(iter + 1, P.max_iterations, rec.rmse, c->user);
+            }
+            break;
+        }
+        if (rec.exit_code == 2) {  // error grew: icpengine.cpp:311-314
+            log_msg(c, "warning: error increased, stopping");
+            break;
+        }
+        if (rec.exit_code == 3) {  // < 3 inliers: icpengine.cpp:319-323 ; CLI :567-570 breaks and writes back
+            log_msg(c, "error: too few valid pairs to estimate a transform");
+            if (variant == ICP_VARIANT_ENGINE) {
+                out->status = ICP_TOO_FEW_INLIERS;
+                *write_back = false;
+            }
+            break;
+        }
+        it.has_angles = 1;
+        angles_of(rec.T_cum, &it.rotation_angle, &it.translation_distance);
+        if (out->history && n_hist < out->history_cap) out->history[n_hist] = it;
+        ++n_hist;
+        last_rmse = rec.rmse;
+        if (c->on_iteration) c->on_iteration(&it, c->user);                                     // icpengine.cpp:366
+        if (c->on_progress) c->on_progress(iter + 1, P.max_iterations, rec.rmse, c->user);     // :367
+    }
+    ICPB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+
+    out->history_len = std::min(n_hist, out->history ? out->history_cap : 0);
+    std::memcpy(out->cumulative_T, T_cum, sizeof T_cum);
+    std::memcpy(out->last_T, T_last, sizeof T_last);
+    if (*write_back) {
+        ICPB_TRY(apply_pending_launch(c, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p, n));  // the last T, if any
+        out->success = 1;
+        out->total_iterations = n_hist;                                  // icpengine.cpp:386
+        out->final_rmse = (variant == ICP_VARIANT_CLI) ? prev_error : (n_hist ? last_rmse : 0.0);
+        const double* F = (variant == ICP_VARIANT_CLI) ? T_last : T_cum;  // CLI: last incremental T (:616-621)
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) out->final_R[3 * i + j] = F[4 * i + j];
+            out->final_t[i] = F[4 * i + 3];
+        }
+    } else {
+        out->success = 0;
+        out->total_iterations = 0;
+        out->final_rmse = 0.0;
+        std::memset(out->final_R, 0, sizeof out->final_R);
+        std::memset(out->final_t, 0, sizeof out->final_t);
+    }
+    out->history_len = n_hist < (out->history ? out->history_cap : 0) ? n_hist : (out->history ? out->history_cap : 0);
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+        out->ms_loop = ms;
+    }
+    return ICP_OK;
+}
+
+static int write_back_source(Ctx* c, double* host_xyz, int64_t n) {
+    ICPB_TRY(devbuf_reserve(c, c->scratch1, (size_t)n * 3 * sizeof(double)));
+    ICPB_TRY(unsort_launch(c, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p,
+                           c->src_identity_perm ? nullptr : (uint32_t*)c->sperm.p, n, (double*)c->scratch1.p));
+    ICPB_CUDA(c, cudaMemcpyAsync(host_xyz, c->scratch1.p, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ICP_OK;
+}
+
+static void init_result(icp_result* out) {
+    icp_iteration* h = out->history;
+    int cap = out->history_cap;
+    std::memset(out, 0, sizeof *out);
+    out->history = h;
+    out->history_cap = h ? cap : 0;
+    identity16(out->cumulative_T);
+    identity16(out->last_T);
+}
+
+static int register_impl(Ctx* c, double* src_xyz, int64_t n_src, int64_t n_src_global, const double* tgt_xyz, int64_t n_tgt,
+                         icp_result* out, const volatile int* stop_flag) {
+    init_result(out);
+    if (!src_xyz || !tgt_xyz || n_src_global <= 0 || n_tgt <= 0) {  // icpengine.cpp:26-34
+        out->status = ICP_EMPTY_INPUT;
+        return ICP_EMPTY_INPUT;
+    }
+    ICPB_CUDA(c, cudaSetDevice(c->device));
+    const icp_params& P = c->params;
+    const int leaf = (P.variant == ICP_VARIANT_CLI) ? 10 : P.octree_max_points;  // icp_registration.cpp:454
+    const int depth = (P.variant == ICP_VARIANT_CLI) ? 20 : P.octree_max_depth;
+    log_msg(c, "========== ICP registration start ==========");
+    log_msg(c, "source: %lld points", (long long)n_src_global);
+    log_msg(c, "target: %lld points", (long long)n_tgt);
+
+    ICPB_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+    ICPB_TRY(upload(c, c->tgt_raw, tgt_xyz, n_tgt));
+    c->n_tgt = n_tgt;
+    DevBuf& src_stage = c->scratch_src;
+    if (n_src > 0) ICPB_TRY(upload(c, src_stage, src_xyz, n_src));
+    ICPB_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+    log_msg(c, "building the target octree ...");
+    ICPB_TRY(octree_build_device(c, (const double*)c->tgt_raw.p, n_tgt, leaf, depth));
+    log_msg(c, "octree built: %lld nodes, %lld leaves, depth %d", (long long)c->tree.n_nodes, (long long)c->tree.n_leaves,
+            c->tree.depth);
+    c->src_identity_perm = false;
+    c->n_src = n_src;
+    if (n_src > 0) ICPB_TRY(source_from_device_aos(c, (const double*)src_stage.p, n_src));
+    ICPB_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
+
+    bool write_back = true;
+    ICPB_TRY(run_loop(c, n_src_global, out, stop_flag, &write_back));
+    ICPB_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
+    if (write_back && n_src > 0) ICPB_TRY(write_back_source(c, src_xyz, n_src));  // icpengine.cpp:371-375
+    cudaEvent_t end;
+    ICPB_CUDA(c, cudaEventCreate(&end));
+    ICPB_CUDA(c, cudaEventRecord(end, c->stream));
+    ICPB_CUDA(c, cudaEventSynchronize(end));
+    cudaEventElapsedTime(&out->ms_h2d, c->ev[4], c->ev[5]);
+    cudaEventElapsedTime(&out->ms_build, c->ev[5], c->ev[6]);
+    cudaEventElapsedTime(&out->ms_d2h, c->ev[7], end);
+    cudaEventDestroy(end);
+    if (out->status == ICP_OK) {
+        log_msg(c, "========== registration finished ==========");
+        log_msg(c, "total iterations: %d", out->total_iterations);
+        log_msg(c, "final RMSE: %.6f", out->final_rmse);
+    }
+    return out->status;
+}
+
+}  // namespace icpb
+
+using namespace icpb;
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int icp_abi_version(void) { return ICP_B200_ABI_VERSION; }
+
+void icp_default_params(icp_params* p) {
+    if (!p) return;
+    p->max_iterations = 50;
+    p->tolerance = 1e-6;
+    p->sigma_multiplier = 3.0;
+    p->octree_max_points = 10;
+    p->octree_max_depth = 20;
+    p->variant = ICP_VARIANT_ENGINE;
+}
+
+int icp_create(icp_handle* out, int device_id) {
+    if (!out) return ICP_INVALID_ARGUMENT;
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device_id < 0 || device_id >= n_dev) {
+        cudaGetLastError();
+        return ICP_CUDA_ERROR;  // no CPU fallback: without a CUDA device the library refuses to work
+    }
+    Ctx* c = new (std::nothrow) Ctx();
+    if (!c) return ICP_CUDA_ERROR;
+    c->device = device_id;
+    icp_default_params(&c->params);
+    if (cudaSetDevice(device_id) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    for (auto& e : c->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    if (cudaMalloc(&c->d_state, sizeof(LoopState)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    if (cudaHostAlloc(&c->h_rec, sizeof(IterRecord), cudaHostAllocMapped) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    if (cudaHostGetDevicePointer(&c->d_rec, c->h_rec, 0) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    const char* m = getenv("ICP_B200_NN_MODE");
+    if (m) c->opt_nn_mode = atoi(m) ? 1 : 0;
+    *out = (icp_handle)c;
+    return ICP_OK;
+}
+
+void icp_destroy(icp_handle h) {
+    Ctx* c = (Ctx*)h;
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    icp_comm_destroy(h);
+    octree_free(c);
+    DevBuf* bufs[] = {&c->tgt_raw, &c->sx, &c->sy, &c->sz, &c->sperm, &c->pos, &c->dist, &c->mask, &c->part_a, &c->part_b,
+                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b};
+    for (DevBuf* b : bufs) devbuf_free(*b);
+    if (c->d_state) cudaFree(c->d_state);
+    if (c->h_rec) cudaFreeHost(c->h_rec);
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c->nccl;
+    delete c;
+}
+
+const char* icp_last_error(icp_handle h) {
+    Ctx* c = (Ctx*)h;
+    return c ? c->err.c_str() : "null handle";
+}
+
+int icp_set_params(icp_handle h, const icp_params* p) {
+    Ctx* c = (Ctx*)h;
+    if (!c || !p) return ICP_INVALID_ARGUMENT;
+    if (p->variant != ICP_VARIANT_ENGINE && p->variant != ICP_VARIANT_CLI) {
+        c->err = "params: unknown variant";
+        return ICP_INVALID_ARGUMENT;
+    }
+    if (p->octree_max_depth < 0 || p->octree_max_depth > 21) {
+        c->err = "params: octree_max_depth must be in [0,21] (3 bits per level in a 64-bit key)";
+        return ICP_INVALID_ARGUMENT;
+    }
+    c->params = *p;
+    return ICP_OK;
+}
+
+int icp_get_params(icp_handle h, icp_params* p) {
+    Ctx* c = (Ctx*)h;
+    if (!c || !p) return ICP_INVALID_ARGUMENT;
+    *p = c->params;
+    return ICP_OK;
+}
+
+int icp_set_callbacks(icp_handle h, icp_iteration_cb on_iteration, icp_progress_cb on_progress, icp_log_cb on_log, void* user) {
+    Ctx* c = (Ctx*)h;
+    if (!c) return ICP_INVALID_ARGUMENT;
+    c->on_iteration = on_iteration;
+    c->on_progress = on_progress;
+    c->on_log = on_log;
+    c->user = user;
+    return ICP_OK;
+}
+
+int icp_set_option(icp_handle h, const char* key, double value) {
+    Ctx* c = (Ctx*)h;
+    if (!c || !key) return ICP_INVALID_ARGUMENT;
+    if (!strcmp(key, "nn_mode")) c->opt_nn_mode = value != 0.0 ? 1 : 0;
+    else if (!strcmp(key, "order_queries")) c->opt_order_queries = value != 0.0;
+    else if (!strcmp(key, "write_mask")) c->opt_write_mask = value != 0.0;
+    else {
+        c->err = std::string("unknown option ") + key;
+        return ICP_INVALID_ARGUMENT;
+    }
+    return ICP_OK;
+}
+
+int64_t icp_kernel_launches(icp_handle h) {
+    Ctx* c = (Ctx*)h;
+    return c ? c->launches : 0;
+}
+
+int icp_register(icp_handle h, double* src_xyz, int64_t n_src, const double* tgt_xyz, int64_t n_tgt, icp_result* out,
+                 const volatile int* stop_flag) {
+    Ctx* c = (Ctx*)h;
+    if (!c || !out) return ICP_INVALID_ARGUMENT;
+    if (c->n_ranks > 1) {
+        c->err = "icp_register on a handle with an initialised communicator: use icp_register_sharded";
+        return ICP_INVALID_ARGUMENT;
+    }
+    return register_impl(c, src_xyz, n_src, n_src, tgt_xyz, n_tgt, out, stop_flag);
+}
+
+int icp_register_sharded(icp_handle h, double* src_shard_xyz, int64_t n_shard, int64_t n_src_global, const double* tgt_xyz,
+                         int64_t n_tgt, icp_result* out, const volatile int* stop_flag) {
+    Ctx* c = (Ctx*)h;
+    if (!c || !out) return ICP_INVALID_ARGUMENT;
+    return register_impl(c, src_shard_xyz, n_shard, n_src_global, tgt_xyz, n_tgt, out, stop_flag);
+}
+
+int icp_octree_build(icp_handle h, const double* tgt_xyz, int64_t n_tgt, int max_points, int max_depth) {
+    Ctx* c = (Ctx*)h;
+    if (!c) return ICP_INVALID_ARGUMENT;
+    if (!tgt_xyz || n_tgt <= 0) return ICP_EMPTY_INPUT;
+    ICPB_CUDA(c, cudaSetDevice(c->device));
+    ICPB_TRY(upload(c, c->tgt_raw, tgt_xyz, n_tgt));
+    c->n_tgt = n_tgt;
+    ICPB_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+    ICPB_TRY(octree_build_device(c, (const double*)c->tgt_raw.p, n_tgt, max_points, max_depth));
+    ICPB_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->last_build_ms, c->ev[5], c->ev[6]);
+    return ICP_OK;
+}
+
+int icp_octree_get_info(icp_handle h, icp_octree_info* info) {
+    Ctx* c = (Ctx*)h;
+    if (!c || !info) return ICP_INVALID_ARGUMENT;
+    if (!c->tree.valid) return ICP_NO_OCTREE;
+    const DeviceOctree& t = c->tree;
+    std::memset(info, 0, sizeof *info);
+    info->n_points = t.n_pts;
+    info->n_nodes = t.n_nodes;
+    info->n_leaves = t.n_leaves;
+    info->node_bytes = t.n_nodes * (int64_t)sizeof(Node);
+    info->point_bytes = t.n_pts * (int64_t)sizeof(TPoint);
+    info->depth = t.depth;
+    info->max_points = t.max_pts;
+    info->max_depth = t.max_depth;
+    for (int a = 0; a < 3; ++a) {
+        info->root_lo[a] = t.root_lo[a];
+        info->root_hi[a] = t.root_hi[a];
+    }
+    info->build_ms = c->last_build_ms;
+    return ICP_OK;
+}
+
+int icp_octree_dump(icp_handle h, int64_t* n_nodes_out, int64_t* n_leaf_points_out, int32_t* depth, uint64_t* key,
+                    uint8_t* is_leaf, int32_t* count, double* box6, int32_t* leaf_idx) {
+    Ctx* c = (Ctx*)h;
+    if (!c) return ICP_INVALID_ARGUMENT;
+    if (!c->tree.valid) return ICP_NO_OCTREE;
+    const DeviceOctree& t = c->tree;
+    if (n_nodes_out) *n_nodes_out = t.n_nodes;
+    if (n_leaf_points_out) *n_leaf_points_out = t.n_pts;
+    if (!depth) return ICP_OK;
+    ICPB_CUDA(c, cudaSetDevice(c->device));
+    std::vector<Node> nodes((size_t)t.n_nodes);
+    std::vector<TPoint> pts((size_t)t.n_pts);
+    ICPB_CUDA(c, cudaMemcpy(nodes.data(), t.nodes, nodes.size() * sizeof(Node), cudaMemcpyDeviceToHost));
+    ICPB_CUDA(c, cudaMemcpy(pts.data(), t.pts, pts.size() * sizeof(TPoint), cudaMemcpyDeviceToHost));
+    // pre-order walk, children in octant order; leaf indices ascending (the reference's leaf lists are)
+    struct Item { uint32_t node; uint64_t key; };
+    std::vector<Item> stack;
+    stack.push_back({0u, 0ull});
+    int64_t slot = 0, nidx = 0;
+    while (!stack.empty()) {
+        Item it = stack.back();
+        stack.pop_back();
+        const Node& nd = nodes[it.node];
+        const uint32_t mask = nd.meta & 0xFFu;
+        depth[slot] = (int32_t)((nd.meta >> 8) & 0xFFu);
+        key[slot] = it.key;
+        is_leaf[slot] = mask == 0 ? 1 : 0;
+        count[slot] = mask == 0 ? (int32_t)nd.npts : 0;
+        double* b = box6 + 6 * slot;
+        b[0] = nd.lo[0]; b[1] = nd.hi[0]; b[2] = nd.lo[1]; b[3] = nd.hi[1]; b[4] = nd.lo[2]; b[5] = nd.hi[2];
+        ++slot;
+        if (mask == 0) {
+            for (uint32_t k = 0; k < nd.npts; ++k) leaf_idx[nidx + k] = (int32_t)pts[nd.pt0 + k].idx;
+            std::sort(leaf_idx + nidx, leaf_idx + nidx + nd.npts);
+            nidx += nd.npts;
+        } else {
+            int nch = __builtin_popcount(mask);
+            for (int o = 7; o >= 0; --o)
+                if ((mask >> o) & 1u) {
+                    --nch;
+                    stack.push_back({nd.child0 + (uint32_t)nch, (it.key << 3) | (uint64_t)o});
+                }
+        }
+    }
+    return ICP_OK;
+}
+
+int icp_nn_query(icp_handle h, const double* q_xyz, int64_t n, int32_t* idx_out, double* dist_out, float* kernel_ms) {
+    Ctx* c = (Ctx*)h;
+    if (!c) return ICP_INVALID_ARGUMENT;
+    if (!c->tree.valid) return ICP_NO_OCTREE;
+    if (n <= 0) return ICP_OK;
+    if (!q_xyz || !idx_out) return ICP_INVALID_ARGUMENT;
+    ICPB_CUDA(c, cudaSetDevice(c->device));
+    ICPB_TRY(upload(c, c->scratch_src, q_xyz, n));
+    c->src_identity_perm = false;
+    ICPB_TRY(source_from_device_aos(c, (const double*)c->scratch_src.p, n));
+    ICPB_TRY(ensure_run_buffers(c, n));
+    NNLaunch L;
+    L.sx = (double*)c->sx.p; L.sy = (double*)c->sy.p; L.sz = (double*)c->sz.p;
+    L.ox = L.oy = L.oz = nullptr;
+    L.n = n;
+    L.pos_out = (uint32_t*)c->pos.p;
+    L.dist_out = (double*)c->dist.p;
+    L.prev_pos = nullptr;
+    L.part_a = nullptr;
+    L.state = nullptr;
+    L.apply_pending = 0;
+    L.mode = c->opt_nn_mode;
+    L.init_best = (c->params.variant == ICP_VARIANT_CLI) ? 1e20 : DBL_MAX;
+    ICPB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    ICPB_TRY(nn_launch(c, L));
+    ICPB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    // results back in caller order
+    ICPB_TRY(devbuf_reserve(c, c->scratch1, (size_t)n * (sizeof(int32_t) + sizeof(double))));
+    double* d_dist = (double*)c->scratch1.p;
+    int32_t* d_idx = (int32_t*)(d_dist + n);
+    ICPB_TRY(unsort_results_launch(c, L.pos_out, L.dist_out, c->src_identity_perm ? nullptr : (uint32_t*)c->sperm.p, n, d_idx, d_dist));
+    ICPB_CUDA(c, cudaMemcpyAsync(idx_out, d_idx, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (dist_out) ICPB_CUDA(c, cudaMemcpyAsync(dist_out, d_dist, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (kernel_ms) cudaEventElapsedTime(kernel_ms, c->ev[0], c->ev[1]);
+    return ICP_OK;
+}
+
+int icp_iteration_stats(icp_handle h, const double* src_xyz, int64_t n, const int32_t* idx, int iteration, double* dist_out,
+                        uint8_t* inlier_mask_out, icp_stats* stats_out) {
+    Ctx* c = (Ctx*)h;
+    if (!c) return ICP_INVALID_ARGUMENT;
+    if (!c->tree.valid) return ICP_NO_OCTREE;
+    if (!src_xyz || !idx || n <= 0) return ICP_EMPTY_INPUT;
+    ICPB_CUDA(c, cudaSetDevice(c->device));
+    ICPB_TRY(build_inv_perm(c));
+    ICPB_TRY(upload(c, c->scratch_src, src_xyz, n));
+    ICPB_TRY(ensure_source_buffers(c, n));
+    ICPB_TRY(ensure_run_buffers(c, n));
+    c->n_src = n;
+    c->src_identity_perm = true;
+    double *sx = (double*)c->sx.p, *sy = (double*)c->sy.p, *sz = (double*)c->sz.p;
+    ICPB_TRY(aos_to_soa_launch(c, (const double*)c->scratch_src.p, n, sx, sy, sz));
+    ICPB_TRY(devbuf_reserve(c, c->scratch1, (size_t)n * sizeof(int32_t)));
+    ICPB_CUDA(c, cudaMemcpyAsync(c->scratch1.p, idx, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    LoopState hs;
+    std::memset(&hs, 0, sizeof hs);
+    hs.prev_error = 1e10;
+    identity16(hs.T_pending); identity16(hs.T_last); identity16(hs.T_cum);
+    for (int a = 0; a < 3; ++a) hs.pivot_a[a] = hs.pivot_b[a] = 0.5 * (c->tree.root_lo[a] + c->tree.root_hi[a]);
+    hs.tolerance = c->params.tolerance;
+    hs.sigma = (c->params.variant == ICP_VARIANT_CLI) ? 3.0 : c->params.sigma_multiplier;
+    hs.variant = c->params.variant;
+    hs.max_iterations = c->params.max_iterations;
+    hs.n_global = n;
+    ICPB_CUDA(c, cudaMemcpyAsync(c->d_state, &hs, sizeof hs, cudaMemcpyHostToDevice, c->stream));
+    StatA* part_a = (StatA*)c->part_a.p + 64;
+    StatA* rank_a = (StatA*)c->gather_a.p;
+    double* rank_b = (double*)c->gather_b.p;
+    int n_part = 0;
+    ICPB_TRY(dist_from_idx_launch(c, sx, sy, sz, (const int32_t*)c->scratch1.p, n, (uint32_t*)c->pos.p, (double*)c->dist.p, part_a,
+                                  &n_part));
+    ICPB_TRY(stage_a_finish(c, part_a, n_part, rank_a, rank_a, 1, iteration, true));
+    ICPB_TRY(stage_b_launch(c, sx, sy, sz, (uint32_t*)c->pos.p, (double*)c->dist.p, n, (uint8_t*)c->mask.p, (double*)c->part_b.p, rank_b));
+    ICPB_TRY(solve_launch(c, rank_b, 1));
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    const IterRecord rec = *c->h_rec;
+    if (dist_out) ICPB_CUDA(c, cudaMemcpy(dist_out, c->dist.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (inlier_mask_out) ICPB_CUDA(c, cudaMemcpy(inlier_mask_out, c->mask.p, (size_t)n, cudaMemcpyDeviceToHost));
+    if (stats_out) {
+        double b17[STATB_DOUBLES];
+        ICPB_CUDA(c, cudaMemcpy(b17, rank_b, sizeof b17, cudaMemcpyDeviceToHost));
+        stats_out->min_distance = rec.dmin;
+        stats_out->max_distance = rec.dmax;
+        stats_out->mean = rec.mean;
+        stats_out->std_dev = rec.std_dev;
+        stats_out->threshold = rec.threshold;
+        stats_out->rmse = rec.rmse;
+        stats_out->sum_sq = b17[1];
+        stats_out->problem_count = (int64_t)rec.problems;
+        stats_out->valid_count = rec.valid_points;
+        stats_out->outlier_count = rec.outlier_points;
+    }
+    return ICP_OK;
+}
+
+int icp_best_fit_transform(icp_handle h, const double* a_xyz, const double* b_xyz, int64_t n, double* T_out) {
+    Ctx* c = (Ctx*)h;
+    if (!c || !T_out) return ICP_INVALID_ARGUMENT;
+    if (!a_xyz || !b_xyz || n <= 0) return ICP_EMPTY_INPUT;
+    ICPB_CUDA(c, cudaSetDevice(c->device));
+    ICPB_TRY(devbuf_reserve(c, c->scratch1, (size_t)n * 6 * sizeof(double) + 1024));
+    double* da = (double*)c->scratch1.p;
+    double* db = da + 3 * n;
+    ICPB_CUDA(c, cudaMemcpyAsync(da, a_xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    ICPB_CUDA(c, cudaMemcpyAsync(db, b_xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    ICPB_TRY(devbuf_reserve(c, c->part_b, (size_t)(stage_b_blocks(c, n) + 8) * STATB_DOUBLES * sizeof(double)));
+    ICPB_TRY(devbuf_reserve(c, c->gather_b, (size_t)(STATB_DOUBLES + 16) * sizeof(double) + 64));
+    double* sums = (double*)c->gather_b.p;
+    ICPB_TRY(pairs_b_launch(c, da, db, n, (double*)c->part_b.p, sums));
+    ICPB_TRY(bestfit_launch(c, sums, da, db, sums + STATB_DOUBLES));
+    ICPB_CUDA(c, cudaMemcpyAsync(T_out, sums + STATB_DOUBLES, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ICP_OK;
+}
+
+int icp_solve_from_H(icp_handle h, const double* H9, const double* cA3, const double* cB3, double* T_out, double* U9, double* S3,
+                     double* V9) {
+    Ctx* c = (Ctx*)h;
+    if (!c || !H9 || !cA3 || !cB3 || !T_out) return ICP_INVALID_ARGUMENT;
+    ICPB_CUDA(c, cudaSetDevice(c->device));
+    ICPB_TRY(devbuf_reserve(c, c->scratch0, 64 * sizeof(double)));
+    double in[15], outv[37];
+    std::memcpy(in, H9, 9 * sizeof(double));
+    std::memcpy(in + 9, cA3, 3 * sizeof(double));
+    std::memcpy(in + 12, cB3, 3 * sizeof(double));
+    double* d = (double*)c->scratch0.p;
+    ICPB_CUDA(c, cudaMemcpyAsync(d, in, sizeof in, cudaMemcpyHostToDevice, c->stream));
+    ICPB_TRY(solve_from_H_launch(c, d, d + 16));
+    ICPB_CUDA(c, cudaMemcpyAsync(outv, d + 16, sizeof outv, cudaMemcpyDeviceToHost, c->stream));
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::memcpy(T_out, outv, 16 * sizeof(double));
+    if (U9) std::memcpy(U9, outv + 16, 9 * sizeof(double));
+    if (S3) std::memcpy(S3, outv + 25, 3 * sizeof(double));
+    if (V9) std::memcpy(V9, outv + 28, 9 * sizeof(double));
+    return ICP_OK;
+}
+
+int icp_apply_transform(icp_handle h, const double* T16, double* xyz, int64_t n) {
+    Ctx* c = (Ctx*)h;
+    if (!c || !T16) return ICP_INVALID_ARGUMENT;
+    if (n <= 0) return ICP_OK;
+    if (!xyz) return ICP_INVALID_ARGUMENT;
+    ICPB_CUDA(c, cudaSetDevice(c->device));
+    ICPB_TRY(upload(c, c->scratch_src, xyz, n));
+    ICPB_TRY(devbuf_reserve(c, c->scratch0, 64 * sizeof(double)));
+    ICPB_CUDA(c, cudaMemcpyAsync(c->scratch0.p, T16, 16 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    ICPB_TRY(apply_aos_launch(c, (const double*)c->scratch0.p, (double*)c->scratch_src.p, n));
+    ICPB_CUDA(c, cudaMemcpyAsync(xyz, c->scratch_src.p, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ICP_OK;
+}
+
+int icp_source_upload(icp_handle h, const double* src_xyz, int64_t n_src) {
+    Ctx* c = (Ctx*)h;
+    if (!c) return ICP_INVALID_ARGUMENT;
+    if (!src_xyz || n_src <= 0) return ICP_EMPTY_INPUT;
+    ICPB_CUDA(c, cudaSetDevice(c->device));
+    ICPB_TRY(upload(c, c->scratch_src, src_xyz, n_src));
+    c->src_identity_perm = false;
+    ICPB_TRY(source_from_device_aos(c, (const double*)c->scratch_src.p, n_src));
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ICP_OK;
+}
+
+int icp_register_resident(icp_handle h, int64_t n_src_global, icp_result* out, double* src_out_xyz, const volatile int* stop_flag) {
+    Ctx* c = (Ctx*)h;
+    if (!c || !out) return ICP_INVALID_ARGUMENT;
+    init_result(out);
+    if (!c->tree.valid) return ICP_NO_OCTREE;
+    if (c->n_src <= 0 && c->n_ranks <= 1) return ICP_EMPTY_INPUT;
+    ICPB_CUDA(c, cudaSetDevice(c->device));
+    bool write_back = true;
+    ICPB_TRY(run_loop(c, n_src_global > 0 ? n_src_global : c->n_src, out, stop_flag, &write_back));
+    if (write_back && src_out_xyz && c->n_src > 0) ICPB_TRY(write_back_source(c, src_out_xyz, c->n_src));
+    return out->status;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------------
+int icp_comm_unique_id(icp_handle h, void* unique_id_128) {
+    Ctx* c = (Ctx*)h;
+    if (!c || !unique_id_128) return ICP_INVALID_ARGUMENT;
+    NcclApi* a = nccl_load(c);
+    if (!a) return ICP_NCCL_ERROR;
+    ncclUniqueId id;
+    ICPB_NCCL(c, a->GetUniqueId(&id));
+    std::memcpy(unique_id_128, &id, sizeof id);
+    return ICP_OK;
+}
+
+int icp_comm_init(icp_handle h, int rank, int n_ranks, const void* unique_id_128) {
+    Ctx* c = (Ctx*)h;
+    if (!c || !unique_id_128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return ICP_INVALID_ARGUMENT;
+    NcclApi* a = nccl_load(c);
+    if (!a) return ICP_NCCL_ERROR;
+    ICPB_CUDA(c, cudaSetDevice(c->device));
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id_128, sizeof id);
+    ncclComm_t comm = nullptr;
+    ICPB_NCCL(c, a->CommInitRank(&comm, n_ranks, id, rank));
+    c->comm = comm;
+    c->rank = rank;
+    c->n_ranks = n_ranks;
+    return ICP_OK;
+}
+
+int icp_comm_destroy(icp_handle h) {
+    Ctx* c = (Ctx*)h;
+    if (!c) return ICP_INVALID_ARGUMENT;
+    if (c->comm && c->nccl) c->nccl->CommDestroy((ncclComm_t)c->comm);
+    c->comm = nullptr;
+    c->rank = 0;
+    c->n_ranks = 1;
+    return ICP_OK;
+}
+
+// ---- batch (BASELINE.json config #5) -------------------------------------------------------------------
+int icp_register_batch(icp_handle h, int32_t n_pairs, double* const* src_xyz, const int64_t* n_src, const double* const* tgt_xyz,
+                       const int64_t* n_tgt, icp_result* results) {
+    Ctx* c = (Ctx*)h;
+    if (!c || n_pairs < 0 || (n_pairs > 0 && (!src_xyz || !n_src || !tgt_xyz || !n_tgt || !results))) return ICP_INVALID_ARGUMENT;
+    int worst = ICP_OK;
+    for (int32_t p = 0; p < n_pairs; ++p) {
+        int s = register_impl(c, src_xyz[p], n_src[p], n_src[p], tgt_xyz[p], n_tgt[p], &results[p], nullptr);
+        if (s == ICP_CUDA_ERROR || s == ICP_NCCL_ERROR) return s;
+        if (s != ICP_OK && worst == ICP_OK) worst = s;
+    }
+    return worst;
+}
+
+}  // extern "C"

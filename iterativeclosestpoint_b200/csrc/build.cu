@@ -1,0 +1,640 @@
+// Target octree construction as a LINEAR octree (replaces Octree::Octree + Octree::buildTree,
+// PointCloudRegistration/core/octree.cpp:41-126; CLI twin icp_registration.cpp:66-104,155-185).
+//
+//   K0  bbox        strict min/max of the target + the 0.001 expansion            (octree.cpp:47-64)
+//   K1  keys        per point, the octant path of buildTree's recursion, obtained by the SAME FP64
+//                   bisection mid = (lo+hi)/2, bit = p > mid, 3 bits per level      (octree.cpp:97-110)
+//   K2  sort        stable LSD radix sort of (key, index), 8 bits per pass
+//   K3  nodes       level-by-level emission of the node table: a prefix with more than max_pts points and
+//                   depth < max_depth is an inner node, otherwise a leaf            (octree.cpp:88)
+//
+// Cell membership is decided by comparisons against bisection midpoints, never by scaling, so every
+// point lands in exactly the reference's leaf and every box is bit-identical to the reference's.
+#include "internal.h"
+#include <algorithm>
+#include <cstring>
+
+namespace icpb {
+
+// ------------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------------
+int devbuf_reserve(Ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return ICP_OK;
+    if (b.p) ICPB_CUDA(c, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    ICPB_CUDA(c, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return ICP_OK;
+}
+
+void devbuf_free(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of uint32 (three kernels; sizes here are at most a few 10^7)
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem_warp, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) smem_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (lane < (int)(blockDim.x >> 5)) ? smem_warp[lane] : 0u;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        smem_warp[lane] = winc - w;  // exclusive warp offsets
+        if (lane == 31) smem_warp[32] = winc;
+    }
+    __syncthreads();
+    uint32_t res = smem_warp[warp] + inc - v;
+    *total = smem_warp[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const uint32_t* __restrict__ in,
+                                                                  uint32_t* __restrict__ out, int64_t n,
+                                                                  uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t sw[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        sum += v[k];
+    }
+    uint32_t total;
+    uint32_t off = block_exclusive_scan(sum, sw, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = off;
+        off += v[k];
+    }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the tile sums in place; writes the grand total
+__global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t* __restrict__ sums, int n, uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t sw[33];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + threadIdx.x;
+        uint32_t v = (i < n) ? sums[i] : 0u;
+        uint32_t tot;
+        uint32_t off = block_exclusive_scan(v, sw, &tot);
+        uint32_t c0 = carry;
+        if (i < n) sums[i] = c0 + off;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c0 + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t* __restrict__ out, int64_t n,
+                                                                const uint32_t* __restrict__ tile_offsets) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    const uint32_t off = tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) out[base + k] += off;
+}
+
+int exclusive_scan_u32(Ctx* c, const uint32_t* d_in, uint32_t* d_out, int64_t n, uint32_t* d_total) {
+    if (n <= 0) {
+        if (d_total) ICPB_CUDA(c, cudaMemsetAsync(d_total, 0, sizeof(uint32_t), c->stream));
+        return ICP_OK;
+    }
+    const int tiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+    ICPB_TRY(devbuf_reserve(c, c->scratch3, (size_t)tiles * sizeof(uint32_t)));
+    uint32_t* sums = (uint32_t*)c->scratch3.p;
+    scan_tiles_kernel<<<tiles, SCAN_THREADS, 0, c->stream>>>(d_in, d_out, n, sums);
+    scan_sums_kernel<<<1, 1024, 0, c->stream>>>(sums, tiles, d_total);
+    scan_add_kernel<<<tiles, SCAN_THREADS, 0, c->stream>>>(d_out, n, sums);
+    c->launches += 3;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: bounding box (octree.cpp:47-64).  min/max are order-independent, so a parallel reduction gives the
+// reference's values exactly; NaN coordinates never replace the running bound there (strict < / >) and
+// are skipped here by fmin/fmax, except that a NaN in point 0 seeds the bound in the reference -- handled
+// in the finishing step.
+// ------------------------------------------------------------------------------------------------
+constexpr int BBOX_THREADS = 256;
+
+__global__ void __launch_bounds__(BBOX_THREADS) bbox_partial_kernel(const double* __restrict__ xyz, int64_t n,
+                                                                    double* __restrict__ part /* [grid][6] */) {
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double v = xyz[3 * i + a];
+            lo[a] = fmin(lo[a], v);
+            hi[a] = fmax(hi[a], v);
+        }
+    }
+    __shared__ double sm[6][BBOX_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) {
+            sm[a][warp] = lo[a];
+            sm[3 + a][warp] = hi[a];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = sm[threadIdx.x][0];
+        for (int w = 1; w < BBOX_THREADS / 32; ++w) v = (threadIdx.x < 3) ? fmin(v, sm[threadIdx.x][w]) : fmax(v, sm[threadIdx.x][w]);
+        part[(int64_t)blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
+__global__ void bbox_finish_kernel(const double* __restrict__ part, int n_part, const double* __restrict__ xyz,
+                                   double* __restrict__ root /* lo[3], hi[3] */) {
+    const int a = threadIdx.x;
+    if (a >= 6) return;
+    double v = part[a];
+    for (int k = 1; k < n_part; ++k) v = (a < 3) ? fmin(v, part[(int64_t)k * 6 + a]) : fmax(v, part[(int64_t)k * 6 + a]);
+    const double p0 = xyz[a % 3];
+    if (p0 != p0) v = p0;  // pts[0] seeds the scan (octree.cpp:47-49): a NaN there sticks
+    const double eps = 0.001;
+    root[a] = (a < 3) ? dsub(v, eps) : dadd(v, eps);  // octree.cpp:61-64
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: octant-path keys by FP64 bisection (octree.cpp:97-110 applied max_depth times)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) morton_keys_kernel(const double* __restrict__ xyz, int64_t n,
+                                                          const double* __restrict__ root, int max_depth,
+                                                          uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double lo[3], hi[3], p[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = root[a];
+        hi[a] = root[3 + a];
+        p[a] = xyz[3 * i + a];
+    }
+    uint64_t key = 0;
+    for (int d = 0; d < max_depth; ++d) {
+        uint32_t oct = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double mid = dmul(dadd(lo[a], hi[a]), 0.5);  // (min+max)/2, exact halving
+            const bool up = p[a] > mid;                        // strict, octree.cpp:106-108
+            oct |= (up ? 1u : 0u) << a;
+            lo[a] = up ? mid : lo[a];
+            hi[a] = up ? hi[a] : mid;
+        }
+        key = (key << 3) | oct;
+    }
+    keys[i] = key;
+    idx[i] = (uint32_t)i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: stable LSD radix sort, 8 bits per pass, (uint64 key, uint32 payload)
+// Each block owns a contiguous tile; each warp a contiguous chunk of the tile, walked in rounds of 32
+// consecutive elements, so ranks follow input order (stability).
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ROUNDS = 16;                            // elements per thread
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;          // 4096 elements per block
+constexpr int RS_CHUNK = 32 * RS_ROUNDS;                 // per warp
+
+__device__ __forceinline__ void warp_digit_hist(const uint64_t* __restrict__ keys, int64_t n, int64_t chunk_base,
+                                                int shift, uint32_t* hist /* smem [256] of this warp */) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll 4
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const int64_t i = chunk_base + (int64_t)r * 32 + lane;
+        const bool ok = i < n;
+        const uint32_t d = ok ? (uint32_t)((keys[i] >> shift) & 0xFF) : 0x100u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        if (ok && (peers & ((1u << lane) - 1u)) == 0) hist[d] += __popc(peers);
+        __syncwarp();
+    }
+}
+
+// hist_out is digit-major: hist_out[d * n_blocks + block]
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift,
+                                                                uint32_t* __restrict__ hist_out, int n_blocks) {
+    __shared__ uint32_t wh[RS_WARPS][256];
+    for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&wh[0][0])[k] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    const int64_t chunk_base = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * RS_CHUNK;
+    warp_digit_hist(keys, n, chunk_base, shift, wh[warp]);
+    __syncthreads();
+    uint32_t s = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) s += wh[w][threadIdx.x];
+    hist_out[(int64_t)threadIdx.x * n_blocks + blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint64_t* __restrict__ keys_in,
+                                                                   const uint32_t* __restrict__ vals_in, int64_t n,
+                                                                   int shift, const uint32_t* __restrict__ hist_scan,
+                                                                   int n_blocks, uint64_t* __restrict__ keys_out,
+                                                                   uint32_t* __restrict__ vals_out) {
+    __shared__ uint32_t wh[RS_WARPS][256];  // per-warp histogram, then per-warp running offset
+    for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&wh[0][0])[k] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t chunk_base = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * RS_CHUNK;
+    warp_digit_hist(keys_in, n, chunk_base, shift, wh[warp]);
+    __syncthreads();
+    {
+        // thread d: exclusive prefix over warps + global base of this block's digit-d run
+        const int d = threadIdx.x;
+        uint32_t run = hist_scan[(int64_t)d * n_blocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            uint32_t cnt = wh[w][d];
+            wh[w][d] = run;
+            run += cnt;
+        }
+    }
+    __syncthreads();
+    uint32_t* off = wh[warp];
+#pragma unroll 4
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const int64_t i = chunk_base + (int64_t)r * 32 + lane;
+        const bool ok = i < n;
+        uint64_t key = 0;
+        uint32_t val = 0;
+        if (ok) {
+            key = keys_in[i];
+            val = vals_in[i];
+        }
+        const uint32_t d = ok ? (uint32_t)((key >> shift) & 0xFF) : 0x100u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t before = __popc(peers & ((1u << lane) - 1u));
+        uint32_t base = 0;
+        if (ok) base = off[d];
+        __syncwarp();
+        if (ok) {
+            const uint32_t dst = base + before;
+            keys_out[dst] = key;
+            vals_out[dst] = val;
+            if (before == 0) off[d] = base + __popc(peers);
+        }
+        __syncwarp();
+    }
+}
+
+static int radix_sort_pairs(Ctx* c, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& vals, uint32_t*& vals_alt,
+                            int64_t n, int key_bits) {
+    const int n_blocks = (int)((n + RS_TILE - 1) / RS_TILE);
+    const int64_t hist_n = (int64_t)256 * n_blocks;
+    ICPB_TRY(devbuf_reserve(c, c->scratch2, (size_t)hist_n * sizeof(uint32_t) * 2));
+    uint32_t* hist = (uint32_t*)c->scratch2.p;
+    uint32_t* hist_scan = hist + hist_n;
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        radix_hist_kernel<<<n_blocks, RS_THREADS, 0, c->stream>>>(keys, n, shift, hist, n_blocks);
+        c->launches++;
+        ICPB_TRY(exclusive_scan_u32(c, hist, hist_scan, hist_n, nullptr));
+        radix_scatter_kernel<<<n_blocks, RS_THREADS, 0, c->stream>>>(keys, vals, n, shift, hist_scan, n_blocks, keys_alt,
+                                                                     vals_alt);
+        c->launches++;
+        std::swap(keys, keys_alt);
+        std::swap(vals, vals_alt);
+    }
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+// gather the target into Morton order: (x, y, z, original index)
+__global__ void __launch_bounds__(256) gather_points_kernel(const double* __restrict__ xyz, const uint32_t* __restrict__ idx,
+                                                            int64_t n, TPoint* __restrict__ out, uint32_t* __restrict__ pos_of_idx0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = idx[i];
+    TPoint p;
+    p.x = xyz[3 * (int64_t)j];
+    p.y = xyz[3 * (int64_t)j + 1];
+    p.z = xyz[3 * (int64_t)j + 2];
+    p.idx = (long long)j;
+    out[i] = p;
+    if (j == 0) *pos_of_idx0 = (uint32_t)i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: node table, one level per step.  A node of level d covers the sorted range [pt0, pt0+npts) whose
+// keys share their top 3d bits.  (octree.cpp:86-126)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lower_bound_octant(const uint64_t* __restrict__ keys, uint32_t lo, uint32_t hi,
+                                                       int shift, uint32_t oct) {
+    // first position in [lo, hi) whose octant at `shift` is >= oct
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        uint32_t o = (uint32_t)((keys[mid] >> shift) & 7u);
+        if (o < oct) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// counts[i] = number of non-empty octants of level node i (0 for leaves)
+__global__ void __launch_bounds__(128) node_count_kernel(const Node* __restrict__ nodes, uint32_t first, uint32_t count,
+                                                         const uint64_t* __restrict__ keys, int level, int max_pts,
+                                                         int max_depth, uint32_t* __restrict__ counts) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const Node& nd = nodes[first + t];
+    uint32_t nchild = 0;
+    if (!(nd.npts <= (uint32_t)max_pts || level >= max_depth)) {  // octree.cpp:88
+        const int shift = 3 * (max_depth - 1 - level);
+        uint32_t b = nd.pt0;
+        const uint32_t end = nd.pt0 + nd.npts;
+        for (uint32_t oct = 1; oct <= 8; ++oct) {
+            uint32_t e = (oct == 8) ? end : lower_bound_octant(keys, b, end, shift, oct);
+            nchild += (e > b) ? 1u : 0u;
+            b = e;
+        }
+    }
+    counts[t] = nchild;
+}
+
+__global__ void __launch_bounds__(128) node_emit_kernel(Node* __restrict__ nodes, uint32_t first, uint32_t count,
+                                                        const uint64_t* __restrict__ keys, int level, int max_pts,
+                                                        int max_depth, const uint32_t* __restrict__ child_off,
+                                                        uint32_t next_first, uint32_t* __restrict__ leaf_counter) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    Node nd = nodes[first + t];
+    if (nd.npts <= (uint32_t)max_pts || level >= max_depth) {
+        nodes[first + t].meta = ((uint32_t)level << 8);  // leaf: empty child mask
+        nodes[first + t].child0 = 0;
+        atomicAdd(leaf_counter, 1u);
+        return;
+    }
+    const int shift = 3 * (max_depth - 1 - level);
+    double mid[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) mid[a] = dmul(dadd(nd.lo[a], nd.hi[a]), 0.5);  // octree.cpp:97-99
+    uint32_t b = nd.pt0;
+    const uint32_t end = nd.pt0 + nd.npts;
+    uint32_t mask = 0, k = 0;
+    const uint32_t c0 = next_first + child_off[t];
+    for (uint32_t oct = 0; oct < 8; ++oct) {
+        const uint32_t e = (oct == 7) ? end : lower_bound_octant(keys, b, end, shift, oct + 1);
+        if (e > b) {
+            Node ch;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {  // octree.cpp:115-120
+                const bool up = (oct >> a) & 1u;
+                ch.lo[a] = up ? mid[a] : nd.lo[a];
+                ch.hi[a] = up ? nd.hi[a] : mid[a];
+            }
+            ch.child0 = 0;
+            ch.pt0 = b;
+            ch.npts = e - b;
+            ch.meta = ((uint32_t)(level + 1) << 8);
+            nodes[c0 + k] = ch;
+            mask |= 1u << oct;
+            ++k;
+        }
+        b = e;
+    }
+    nodes[first + t].child0 = c0;
+    nodes[first + t].meta = ((uint32_t)level << 8) | mask;
+}
+
+__global__ void root_node_kernel(Node* __restrict__ nodes, const double* __restrict__ root, uint32_t n) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Node r;
+    for (int a = 0; a < 3; ++a) {
+        r.lo[a] = root[a];
+        r.hi[a] = root[3 + a];
+    }
+    r.child0 = 0;
+    r.pt0 = 0;
+    r.npts = n;
+    r.meta = 0;
+    nodes[0] = r;
+}
+
+__global__ void inv_perm_kernel(const TPoint* __restrict__ pts, int64_t n, uint32_t* __restrict__ inv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[(uint32_t)pts[i].idx] = (uint32_t)i;
+}
+
+void octree_free(Ctx* c) {
+    DeviceOctree& t = c->tree;
+    if (t.nodes) cudaFree(t.nodes);
+    if (t.pts) cudaFree(t.pts);
+    if (t.inv_perm) cudaFree(t.inv_perm);
+    t = DeviceOctree();
+}
+
+static int grow_nodes(Ctx* c, int64_t need) {
+    DeviceOctree& t = c->tree;
+    if (need <= t.cap_nodes) return ICP_OK;
+    int64_t cap = std::max<int64_t>(need + need / 2, 1024);
+    Node* nn = nullptr;
+    ICPB_CUDA(c, cudaMalloc(&nn, (size_t)cap * sizeof(Node)));
+    if (t.nodes) {
+        ICPB_CUDA(c, cudaMemcpyAsync(nn, t.nodes, (size_t)t.n_nodes * sizeof(Node), cudaMemcpyDeviceToDevice, c->stream));
+        ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+        ICPB_CUDA(c, cudaFree(t.nodes));
+    }
+    t.nodes = nn;
+    t.cap_nodes = cap;
+    return ICP_OK;
+}
+
+int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int max_depth) {
+    octree_free(c);
+    if (m <= 0) return ICP_EMPTY_INPUT;
+    if (max_depth < 0 || max_depth > 21 || m > 0x7fffffffLL) {
+        c->err = "octree: max_depth must be in [0,21] and n_tgt < 2^31";
+        return ICP_INVALID_ARGUMENT;
+    }
+    DeviceOctree& t = c->tree;
+    t.max_pts = max_pts;
+    t.max_depth = max_depth;
+    t.n_pts = m;
+    cudaStream_t s = c->stream;
+
+    // K0
+    const int bb_blocks = (int)std::min<int64_t>((m + BBOX_THREADS - 1) / BBOX_THREADS, (int64_t)c->sm_count * 8);
+    ICPB_TRY(devbuf_reserve(c, c->scratch0, (size_t)(bb_blocks + 1) * 6 * sizeof(double) + 64));
+    double* d_part = (double*)c->scratch0.p;
+    double* d_root = d_part + (size_t)bb_blocks * 6;
+    bbox_partial_kernel<<<bb_blocks, BBOX_THREADS, 0, s>>>(d_xyz, m, d_part);
+    bbox_finish_kernel<<<1, 32, 0, s>>>(d_part, bb_blocks, d_xyz, d_root);
+    c->launches += 2;
+
+    // K1
+    uint64_t *keys = nullptr, *keys_alt = nullptr;
+    uint32_t *idx = nullptr, *idx_alt = nullptr;
+    ICPB_TRY(devbuf_reserve(c, c->scratch1, (size_t)m * (2 * sizeof(uint64_t) + 2 * sizeof(uint32_t)) + 1024));
+    keys = (uint64_t*)c->scratch1.p;
+    keys_alt = keys + m;
+    idx = (uint32_t*)(keys_alt + m);
+    idx_alt = idx + m;
+    const int kb = (int)((m + 255) / 256);
+    morton_keys_kernel<<<kb, 256, 0, s>>>(d_xyz, m, d_root, max_depth, keys, idx);
+    c->launches++;
+
+    // K2
+    const int key_bits = 3 * max_depth;
+    if (key_bits > 0) ICPB_TRY(radix_sort_pairs(c, keys, keys_alt, idx, idx_alt, m, key_bits));
+
+    // sorted points
+    ICPB_CUDA(c, cudaMalloc(&t.pts, (size_t)m * sizeof(TPoint)));
+    uint32_t* d_misc = nullptr;  // [0] pos_of_idx0, [1] leaf counter, [2] scan total
+    ICPB_TRY(devbuf_reserve(c, c->part_a, 4096));
+    d_misc = (uint32_t*)c->part_a.p;
+    ICPB_CUDA(c, cudaMemsetAsync(d_misc, 0, 64, s));
+    gather_points_kernel<<<kb, 256, 0, s>>>(d_xyz, idx, m, t.pts, d_misc);
+    c->launches++;
+
+    // K3
+    ICPB_TRY(grow_nodes(c, std::max<int64_t>(m / 2, 1024)));
+    root_node_kernel<<<1, 32, 0, s>>>(t.nodes, d_root, (uint32_t)m);
+    c->launches++;
+    t.n_nodes = 1;
+    uint32_t first = 0, count = 1;
+    int level = 0;
+    uint32_t* counts = idx_alt;  // reuse: level sizes never exceed m
+    uint32_t* offs = (uint32_t*)keys_alt;
+    for (;; ++level) {
+        const int nb = (int)((count + 127) / 128);
+        node_count_kernel<<<nb, 128, 0, s>>>(t.nodes, first, count, keys, level, max_pts, max_depth, counts);
+        c->launches++;
+        ICPB_TRY(exclusive_scan_u32(c, counts, offs, count, d_misc + 2));
+        uint32_t n_children = 0;
+        ICPB_CUDA(c, cudaMemcpyAsync(&n_children, d_misc + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        ICPB_CUDA(c, cudaStreamSynchronize(s));
+        const uint32_t next_first = first + count;
+        ICPB_TRY(grow_nodes(c, (int64_t)next_first + n_children));
+        node_emit_kernel<<<nb, 128, 0, s>>>(t.nodes, first, count, keys, level, max_pts, max_depth, offs, next_first,
+                                            d_misc + 1);
+        c->launches++;
+        t.n_nodes = (int64_t)next_first + n_children;
+        if (n_children == 0) break;
+        first = next_first;
+        count = n_children;
+    }
+    t.depth = level;
+    uint32_t misc[2];
+    double root[6];
+    ICPB_CUDA(c, cudaMemcpyAsync(misc, d_misc, sizeof misc, cudaMemcpyDeviceToHost, s));
+    ICPB_CUDA(c, cudaMemcpyAsync(root, d_root, sizeof root, cudaMemcpyDeviceToHost, s));
+    ICPB_CUDA(c, cudaStreamSynchronize(s));
+    ICPB_CUDA(c, cudaGetLastError());
+    t.pos_of_idx0 = misc[0];
+    t.n_leaves = misc[1];
+    for (int a = 0; a < 3; ++a) {
+        t.root_lo[a] = root[a];
+        t.root_hi[a] = root[3 + a];
+    }
+    t.valid = true;
+    return ICP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Query ordering: the NN kernel runs one query per thread, so neighbouring threads should walk the same
+// nodes.  Queries are ordered by a 3x21-bit Morton code of their own bounding box (this is only a
+// permutation for locality -- any order gives the same per-query answer).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) query_keys_kernel(const double* __restrict__ xyz, int64_t n,
+                                                         const double* __restrict__ box, uint64_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = 0;
+    uint32_t q[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double lo = box[a], hi = box[3 + a];
+        double f = (xyz[3 * i + a] - lo) / (hi - lo);
+        if (!(f > 0.0)) f = 0.0;  // also catches NaN
+        if (f > 1.0) f = 1.0;
+        q[a] = (uint32_t)(f * 2097151.0);
+    }
+    for (int b = 20; b >= 0; --b)
+        key = (key << 3) | (((q[0] >> b) & 1u)) | (((q[1] >> b) & 1u) << 1) | (((q[2] >> b) & 1u) << 2);
+    keys[i] = key;
+    idx[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) gather_soa_kernel(const double* __restrict__ xyz, const uint32_t* __restrict__ idx,
+                                                         int64_t n, double* __restrict__ sx, double* __restrict__ sy,
+                                                         double* __restrict__ sz, uint32_t* __restrict__ perm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = idx[i];
+    sx[i] = xyz[3 * (int64_t)j];
+    sy[i] = xyz[3 * (int64_t)j + 1];
+    sz[i] = xyz[3 * (int64_t)j + 2];
+    perm[i] = j;
+}
+
+int order_queries(Ctx* c, const double* d_q, int64_t n, double* sx, double* sy, double* sz, uint32_t* perm) {
+    cudaStream_t s = c->stream;
+    const int bb_blocks = (int)std::min<int64_t>((n + BBOX_THREADS - 1) / BBOX_THREADS, (int64_t)c->sm_count * 8);
+    ICPB_TRY(devbuf_reserve(c, c->scratch0, (size_t)(bb_blocks + 1) * 6 * sizeof(double) + 64));
+    double* d_part = (double*)c->scratch0.p;
+    double* d_box = d_part + (size_t)bb_blocks * 6;
+    bbox_partial_kernel<<<bb_blocks, BBOX_THREADS, 0, s>>>(d_q, n, d_part);
+    bbox_finish_kernel<<<1, 32, 0, s>>>(d_part, bb_blocks, d_q, d_box);
+    ICPB_TRY(devbuf_reserve(c, c->scratch1, (size_t)n * (2 * sizeof(uint64_t) + 2 * sizeof(uint32_t)) + 1024));
+    uint64_t* keys = (uint64_t*)c->scratch1.p;
+    uint64_t* keys_alt = keys + n;
+    uint32_t* idx = (uint32_t*)(keys_alt + n);
+    uint32_t* idx_alt = idx + n;
+    const int kb = (int)((n + 255) / 256);
+    query_keys_kernel<<<kb, 256, 0, s>>>(d_q, n, d_box, keys, idx);
+    c->launches += 3;
+    ICPB_TRY(radix_sort_pairs(c, keys, keys_alt, idx, idx_alt, n, 63));
+    gather_soa_kernel<<<kb, 256, 0, s>>>(d_q, idx, n, sx, sy, sz, perm);
+    c->launches++;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+int build_inv_perm(Ctx* c) {
+    DeviceOctree& t = c->tree;
+    if (t.inv_perm) return ICP_OK;
+    ICPB_CUDA(c, cudaMalloc(&t.inv_perm, (size_t)t.n_pts * sizeof(uint32_t)));
+    inv_perm_kernel<<<(int)((t.n_pts + 255) / 256), 256, 0, c->stream>>>(t.pts, t.n_pts, t.inv_perm);
+    c->launches++;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+}  // namespace icpb

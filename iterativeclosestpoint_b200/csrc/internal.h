@@ -1,0 +1,128 @@
+// Host-side internals of libicp_b200.so shared between translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "../../include/icp_b200.h"
+
+namespace icpb {
+
+struct DeviceOctree {
+    Node* nodes = nullptr;
+    int64_t n_nodes = 0, cap_nodes = 0;
+    TPoint* pts = nullptr;  // Morton-sorted target points (xyz + original index)
+    int64_t n_pts = 0;
+    int64_t n_leaves = 0;
+    int depth = 0;          // deepest node level
+    int max_pts = 10, max_depth = 20;
+    double root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
+    uint32_t pos_of_idx0 = 0;  // sorted position of original point 0 (findNearest's default answer)
+    uint32_t* inv_perm = nullptr;  // original index -> sorted position (built lazily for the stage API)
+    bool valid = false;
+};
+
+// Reusable device buffer that only grows.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct NcclApi;  // comm.cu
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    std::string err;
+    icp_params params;
+    icp_iteration_cb on_iteration = nullptr;
+    icp_progress_cb on_progress = nullptr;
+    icp_log_cb on_log = nullptr;
+    void* user = nullptr;
+    int64_t launches = 0;
+    int sm_count = 148;
+
+    DeviceOctree tree;
+    DevBuf tgt_raw;  // original-order target AoS (kept for the stage API)
+    int64_t n_tgt = 0;
+
+    // resident source in internal (query-coherent) order
+    DevBuf sx, sy, sz, sperm;  // SoA coordinates + original index of each internal slot
+    int64_t n_src = 0;
+    DevBuf pos, dist, mask;    // per-query NN result (sorted target position), distance, inlier mask
+    DevBuf part_a, part_b;     // per-block partials
+    DevBuf scratch0, scratch1, scratch2, scratch3, scratch_src;
+    bool src_identity_perm = false;  // resident source is in caller order (no permutation)
+    float last_build_ms = 0.f;
+    // tuning knobs (icp_set_option)
+    int opt_nn_mode = 1;             // 0: literal traversal from the root; 1: seeded + subtree start
+    bool opt_order_queries = true;   // Morton-order the source for traversal coherence
+    bool opt_write_mask = false;     // keep the per-point inlier mask of the last iteration
+    LoopState* d_state = nullptr;
+    IterRecord* h_rec = nullptr;  // pinned, device-mapped
+    IterRecord* d_rec = nullptr;
+
+    // multi-GPU
+    NcclApi* nccl = nullptr;
+    void* comm = nullptr;
+    int rank = 0, n_ranks = 1;
+    DevBuf gather_a, gather_b;
+};
+
+#define ICPB_CUDA(ctx, call)                                                                      \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
+                         std::to_string(__LINE__) + ")";                                          \
+            return ICP_CUDA_ERROR;                                                                \
+        }                                                                                         \
+    } while (0)
+
+#define ICPB_TRY(expr)              \
+    do {                            \
+        int s__ = (expr);           \
+        if (s__ != ICP_OK) return s__; \
+    } while (0)
+
+int devbuf_reserve(Ctx* c, DevBuf& b, size_t bytes);
+void devbuf_free(DevBuf& b);
+
+// build.cu
+int octree_build_device(Ctx* c, const double* d_tgt_xyz, int64_t m, int max_pts, int max_depth);
+void octree_free(Ctx* c);
+int exclusive_scan_u32(Ctx* c, const uint32_t* d_in, uint32_t* d_out, int64_t n, uint32_t* d_total);
+// Morton-orders n query points (AoS, device) for traversal coherence: fills SoA coordinates and the
+// permutation (internal slot -> original index).
+int order_queries(Ctx* c, const double* d_q_xyz, int64_t n, double* sx, double* sy, double* sz, uint32_t* perm);
+int build_inv_perm(Ctx* c);
+
+// nn.cu
+struct NNLaunch {
+    const double* sx;
+    const double* sy;
+    const double* sz;      // queries, SoA (may alias the outputs when apply_pending)
+    double* ox;
+    double* oy;
+    double* oz;            // transformed queries written back when apply_pending (may be null otherwise)
+    int64_t n;
+    uint32_t* pos_out;     // sorted target position of the NN
+    double* dist_out;      // distance
+    const uint32_t* prev_pos;  // last iteration's match per query, seeds the search (may be null)
+    StatA* part_a;         // per-block partial (may be null: no statistics)
+    const LoopState* state;  // may be null (stateless query)
+    int apply_pending;     // read state->have_T / T_pending and transform on load
+    int mode;              // 0: literal traversal from the root; 1: seeded + subtree start
+    double init_best;      // DBL_MAX (engine) or 1e20 (CLI)
+};
+int nn_launch(Ctx* c, const NNLaunch& L);
+int nn_grid_blocks(int64_t n);
+
+// iter.cu
+int apply_aos_launch(Ctx* c, const double* d_T16, double* xyz, int64_t n);
+int unsort_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const uint32_t* perm, int64_t n,
+                  double* out_xyz);
+
+}  // namespace icpb

@@ -1,0 +1,690 @@
+// The per-iteration reductions and the Kabsch solve (replaces core/icpengine.cpp:187-346,
+// ICPEngine::computeBestFitTransform :76-115 and Eigen::JacobiSVD<Matrix3d>; CLI twin
+// icp_registration.cpp:389-440,499-603).
+//
+//   stage A   distances -> (count, mean, M2, min, max, problems) by Chan merges in a FIXED tree order
+//             -> mean, population std, threshold (icpengine.cpp:235-255)
+//   stage B   inlier mask d <= thr, inlier count, sum d^2, and first/second moments of the matched pairs
+//             about pivots (icpengine.cpp:263-278, 325-337, 82-90)
+//   solve     RMSE, loop control (icpengine.cpp:287-323), H -> 3x3 two-sided Jacobi SVD in Eigen's exact
+//             operation order -> R = V U^T with reflection fix -> t -> T, T_cum = T * T_cum
+//   apply     src = T * src (icpengine.cpp:345), normally fused into the next NN kernel's load
+//
+// All partial results are combined in an order that depends only on the launch geometry, never on
+// scheduling, so a run is bit-reproducible and every rank of a sharded run derives identical totals.
+#include "internal.h"
+#include <algorithm>
+
+namespace icpb {
+
+constexpr int RED_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------
+// stage A
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ StatA stat_empty() {
+    StatA s;
+    s.n = 0.0; s.mean = 0.0; s.m2 = 0.0; s.dmin = DBL_MAX; s.dmax = 0.0; s.problems = 0.0;
+    return s;
+}
+
+// one block: merges `n_part` partials into out[0] (fixed order: strided per thread, then a binary tree)
+__global__ void __launch_bounds__(RED_THREADS) stage_a_reduce_kernel(const StatA* __restrict__ part, int n_part,
+                                                                     StatA* __restrict__ out) {
+    __shared__ StatA sm[RED_THREADS];
+    // contiguous chunk per thread keeps the merge order = index order
+    const int per = (n_part + RED_THREADS - 1) / RED_THREADS;
+    const int b = threadIdx.x * per, e = min(n_part, b + per);
+    StatA acc = stat_empty();
+    for (int k = b; k < e; ++k) acc = stat_merge(acc, part[k]);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 1; s < RED_THREADS; s <<= 1) {
+        if ((threadIdx.x % (2 * s)) == 0) sm[threadIdx.x] = stat_merge(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sm[0];
+}
+
+// merges the per-rank partials in rank order and derives mean / std / threshold
+__global__ void stage_a_finalize_kernel(LoopState* __restrict__ st, const StatA* __restrict__ rank_part, int n_ranks,
+                                        int iter) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    StatA a = rank_part[0];
+    for (int r = 1; r < n_ranks; ++r) a = stat_merge(a, rank_part[r]);
+    st->a = a;
+    const double N = (double)st->n_global;
+    const double mean = a.mean;                 // = (sum d) / N
+    const double sd = dsqrt(ddiv(a.m2, N));     // population std (icpengine.cpp:241-245)
+    double thr;
+    if (st->variant == ICP_VARIANT_ENGINE && iter == 0) {
+        thr = dadd(mean, stdmax(dmul(st->sigma, sd), dmul(mean, 0.5)));  // icpengine.cpp:250-252
+    } else {
+        thr = dadd(mean, dmul(st->sigma, sd));                            // :254 ; CLI :523
+    }
+    st->mean = mean;
+    st->std_dev = sd;
+    st->threshold = thr;
+    st->iter = iter;
+}
+
+int stage_a_finish(Ctx* c, const StatA* part, int n_part, StatA* rank_part_slot, const StatA* all_rank_parts,
+                   int n_ranks, int iter, bool finalize) {
+    stage_a_reduce_kernel<<<1, RED_THREADS, 0, c->stream>>>(part, n_part, rank_part_slot);
+    c->launches++;
+    if (finalize) {
+        stage_a_finalize_kernel<<<1, 32, 0, c->stream>>>(c->d_state, all_rank_parts, n_ranks, iter);
+        c->launches++;
+    }
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+int stage_a_finalize(Ctx* c, const StatA* all_rank_parts, int n_ranks, int iter) {
+    stage_a_finalize_kernel<<<1, 32, 0, c->stream>>>(c->d_state, all_rank_parts, n_ranks, iter);
+    c->launches++;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+// distances for caller-supplied correspondences (stage API): d_i = |src_i - tgt[idx_i]|, out-of-range idx ->
+// DBL_MAX and a problem (icpengine.cpp:199-204, engine variant only)
+__global__ void __launch_bounds__(RED_THREADS) dist_from_idx_kernel(const double* __restrict__ sx, const double* __restrict__ sy,
+                                                                    const double* __restrict__ sz, const int32_t* __restrict__ idx,
+                                                                    int64_t n, const uint32_t* __restrict__ inv_perm, int64_t m,
+                                                                    const TPoint* __restrict__ pts, int variant,
+                                                                    uint32_t* __restrict__ pos_out, double* __restrict__ dist_out,
+                                                                    StatA* __restrict__ part) {
+    __shared__ StatA sm[RED_THREADS];
+    StatA acc = stat_empty();
+    const int64_t per = (n + (int64_t)gridDim.x * RED_THREADS - 1) / ((int64_t)gridDim.x * RED_THREADS);
+    const int64_t b = ((int64_t)blockIdx.x * RED_THREADS + threadIdx.x) * per;
+    const int64_t e = min(n, b + per);
+    for (int64_t i = b; i < e; ++i) {
+        const int32_t j = idx[i];
+        StatA one = stat_empty();
+        one.n = 1.0;
+        double d;
+        uint32_t pos = 0xFFFFFFFFu;
+        if (j < 0 || (int64_t)j >= m) {
+            d = DBL_MAX;
+            if (variant == ICP_VARIANT_ENGINE) one.problems = 1.0;
+        } else {
+            pos = inv_perm[j];
+            const TPoint p = pts[pos];
+            d = dsqrt(sumsq3(dsub(sx[i], p.x), dsub(sy[i], p.y), dsub(sz[i], p.z)));
+            if (!isfinite(d)) one.problems = 1.0;
+        }
+        one.mean = d;
+        if (isfinite(d) && !(j < 0 || (int64_t)j >= m)) {
+            one.dmin = d;
+            one.dmax = d;
+        }
+        pos_out[i] = pos;
+        dist_out[i] = d;
+        acc = stat_merge(acc, one);
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 1; s < RED_THREADS; s <<= 1) {
+        if ((threadIdx.x % (2 * s)) == 0) sm[threadIdx.x] = stat_merge(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = sm[0];
+}
+
+int dist_from_idx_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const int32_t* idx, int64_t n,
+                         uint32_t* pos_out, double* dist_out, StatA* part, int* n_part) {
+    const int blocks = (int)std::min<int64_t>((n + RED_THREADS - 1) / RED_THREADS, (int64_t)c->sm_count * 4);
+    dist_from_idx_kernel<<<blocks, RED_THREADS, 0, c->stream>>>(sx, sy, sz, idx, n, c->tree.inv_perm, c->tree.n_pts,
+                                                                c->tree.pts, c->params.variant, pos_out, dist_out, part);
+    c->launches++;
+    *n_part = blocks;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage B
+// ------------------------------------------------------------------------------------------------
+struct AccB {
+    double v[STATB_DOUBLES];
+};
+
+__device__ __forceinline__ void accb_zero(AccB& a) {
+#pragma unroll
+    for (int k = 0; k < STATB_DOUBLES; ++k) a.v[k] = 0.0;
+}
+
+__device__ __forceinline__ void accb_add_pair(AccB& acc, double d, double ax, double ay, double az, double bx, double by,
+                                              double bz, const double* pa, const double* pb) {
+    acc.v[0] += 1.0;
+    acc.v[1] += d * d;  // distances[idx] * distances[idx] (icpengine.cpp:271-273)
+    const double a[3] = {ax - pa[0], ay - pa[1], az - pa[2]};
+    const double b[3] = {bx - pb[0], by - pb[1], bz - pb[2]};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        acc.v[2 + r] += a[r];
+        acc.v[5 + r] += b[r];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) acc.v[8 + 3 * r + q] += a[r] * b[q];
+    }
+}
+
+__device__ __forceinline__ void accb_block_reduce(AccB& acc, double* out /* 17 doubles */) {
+    __shared__ double sm[RED_THREADS / 32][STATB_DOUBLES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < STATB_DOUBLES; ++k) {
+        double v = acc.v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sm[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < STATB_DOUBLES) {
+        double v = sm[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < RED_THREADS / 32; ++w) v += sm[w][threadIdx.x];
+        out[threadIdx.x] = v;
+    }
+}
+
+// inlier test + accumulation; each thread owns a contiguous run of queries (fixed geometry => fixed order)
+__global__ void __launch_bounds__(RED_THREADS) stage_b_kernel(const double* __restrict__ sx, const double* __restrict__ sy,
+                                                              const double* __restrict__ sz, const uint32_t* __restrict__ pos,
+                                                              const double* __restrict__ dist, int64_t n,
+                                                              const TPoint* __restrict__ pts, const LoopState* __restrict__ st,
+                                                              uint8_t* __restrict__ mask_out, double* __restrict__ part) {
+    const double thr = st->threshold;
+    double pa[3], pb[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        pa[a] = st->pivot_a[a];
+        pb[a] = st->pivot_b[a];
+    }
+    AccB acc;
+    accb_zero(acc);
+    // block-contiguous tiles, thread-strided inside the tile: coalesced and still a fixed order
+    for (int64_t base = (int64_t)blockIdx.x * RED_THREADS; base < n; base += (int64_t)gridDim.x * RED_THREADS) {
+        const int64_t i = base + threadIdx.x;
+        if (i >= n) break;
+        const double d = dist[i];
+        const uint32_t p = pos[i];
+        const bool ok = (d <= thr) && (p != 0xFFFFFFFFu);  // icpengine.cpp:264-268 (NaN => outlier)
+        if (mask_out) mask_out[i] = ok ? 1 : 0;
+        if (ok) {
+            const TPoint t = pts[p];
+            accb_add_pair(acc, d, sx[i], sy[i], sz[i], t.x, t.y, t.z, pa, pb);
+        }
+    }
+    accb_block_reduce(acc, part + (int64_t)blockIdx.x * STATB_DOUBLES);
+}
+
+// explicit pairs (best-fit stage API): all pairs are inliers, pivots = first pair
+__global__ void __launch_bounds__(RED_THREADS) pairs_b_kernel(const double* __restrict__ a_xyz, const double* __restrict__ b_xyz,
+                                                              int64_t n, double* __restrict__ part) {
+    double pa[3], pb[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        pa[a] = a_xyz[a];
+        pb[a] = b_xyz[a];
+    }
+    AccB acc;
+    accb_zero(acc);
+    for (int64_t base = (int64_t)blockIdx.x * RED_THREADS; base < n; base += (int64_t)gridDim.x * RED_THREADS) {
+        const int64_t i = base + threadIdx.x;
+        if (i >= n) break;
+        accb_add_pair(acc, 0.0, a_xyz[3 * i], a_xyz[3 * i + 1], a_xyz[3 * i + 2], b_xyz[3 * i], b_xyz[3 * i + 1],
+                      b_xyz[3 * i + 2], pa, pb);
+    }
+    accb_block_reduce(acc, part + (int64_t)blockIdx.x * STATB_DOUBLES);
+}
+
+// one block: sums the block partials (fixed order) into out[17]
+__global__ void __launch_bounds__(RED_THREADS) stage_b_reduce_kernel(const double* __restrict__ part, int n_part,
+                                                                     double* __restrict__ out) {
+    __shared__ double sm[RED_THREADS];
+    for (int k = 0; k < STATB_DOUBLES; ++k) {
+        const int per = (n_part + RED_THREADS - 1) / RED_THREADS;
+        const int b = threadIdx.x * per, e = min(n_part, b + per);
+        double v = 0.0;
+        for (int j = b; j < e; ++j) v += part[(int64_t)j * STATB_DOUBLES + k];
+        sm[threadIdx.x] = v;
+        __syncthreads();
+        for (int s = 1; s < RED_THREADS; s <<= 1) {
+            if ((threadIdx.x % (2 * s)) == 0) sm[threadIdx.x] += sm[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[k] = sm[0];
+        __syncthreads();
+    }
+}
+
+int stage_b_blocks(Ctx* c, int64_t n) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>((n + RED_THREADS - 1) / RED_THREADS, (int64_t)c->sm_count * 8));
+}
+
+int stage_b_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const uint32_t* pos, const double* dist,
+                   int64_t n, uint8_t* mask_out, double* part, double* rank_part_slot) {
+    const int blocks = stage_b_blocks(c, n);
+    stage_b_kernel<<<blocks, RED_THREADS, 0, c->stream>>>(sx, sy, sz, pos, dist, n, c->tree.pts, c->d_state, mask_out, part);
+    stage_b_reduce_kernel<<<1, RED_THREADS, 0, c->stream>>>(part, blocks, rank_part_slot);
+    c->launches += 2;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+int pairs_b_launch(Ctx* c, const double* a_xyz, const double* b_xyz, int64_t n, double* part, double* out17) {
+    const int blocks = stage_b_blocks(c, n);
+    pairs_b_kernel<<<blocks, RED_THREADS, 0, c->stream>>>(a_xyz, b_xyz, n, part);
+    stage_b_reduce_kernel<<<1, RED_THREADS, 0, c->stream>>>(part, blocks, out17);
+    c->launches += 2;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 two-sided Jacobi SVD in Eigen 3.3.4's operation order (JacobiSVD.h:663-786, RealSvd2x2.h:19-50,
+// Jacobi.h:83-114,428-440).  Row-major 3x3.  One thread; every operation is IEEE double with no
+// contraction, so given the same H the result equals the reference's bit for bit.
+// ------------------------------------------------------------------------------------------------
+struct Rot {
+    double c, s;
+};
+
+__device__ __forceinline__ void rot_apply(double* x, double* y, int n, int stride, Rot j) {
+    if (j.c == 1.0 && j.s == 0.0) return;  // Jacobi.h:308
+    for (int i = 0; i < n; ++i) {
+        const double xi = x[i * stride], yi = y[i * stride];
+        x[i * stride] = dadd(dmul(j.c, xi), dmul(j.s, yi));
+        y[i * stride] = dadd(dmul(-j.s, xi), dmul(j.c, yi));
+    }
+}
+
+__device__ __forceinline__ Rot make_jacobi(double x, double y, double z) {  // Jacobi.h:83-114
+    Rot r;
+    const double deno = dmul(2.0, fabs(y));
+    if (deno < DBL_MIN) {
+        r.c = 1.0;
+        r.s = 0.0;
+        return r;
+    }
+    const double tau = ddiv(dsub(x, z), deno);
+    const double w = dsqrt(dadd(dmul(tau, tau), 1.0));
+    double t;
+    if (tau > 0.0)
+        t = ddiv(1.0, dadd(tau, w));
+    else
+        t = ddiv(1.0, dsub(tau, w));
+    const double sign_t = t > 0.0 ? 1.0 : -1.0;
+    const double n = ddiv(1.0, dsqrt(dadd(dmul(t, t), 1.0)));
+    r.s = dmul(dmul(dmul(-sign_t, ddiv(y, fabs(y))), fabs(t)), n);
+    r.c = n;
+    return r;
+}
+
+__device__ void svd3(const double* H, double* U, double* S, double* V) {
+    const double precision = 2.0 * DBL_EPSILON;
+    const double consider_as_zero = DBL_MIN;
+    double W[9];
+    double scale = 0.0;
+    for (int i = 0; i < 9; ++i) {
+        const double a = fabs(H[i]);
+        if (a > scale) scale = a;
+    }
+    if (scale == 0.0) scale = 1.0;
+    for (int i = 0; i < 9; ++i) {
+        W[i] = ddiv(H[i], scale);
+        U[i] = V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    }
+    double max_diag = fabs(W[0]);
+    if (fabs(W[4]) > max_diag) max_diag = fabs(W[4]);
+    if (fabs(W[8]) > max_diag) max_diag = fabs(W[8]);
+    bool finished = false;
+    int guard = 0;
+    while (!finished && guard++ < 1000) {
+        finished = true;
+        for (int p = 1; p < 3; ++p)
+            for (int q = 0; q < p; ++q) {
+                const double pm = dmul(precision, max_diag);
+                const double thr = (consider_as_zero < pm) ? pm : consider_as_zero;
+                if (fabs(W[3 * p + q]) > thr || fabs(W[3 * q + p]) > thr) {
+                    finished = false;
+                    // real_2x2_jacobi_svd on the (p,q) block
+                    double m[4] = {W[3 * p + p], W[3 * p + q], W[3 * q + p], W[3 * q + q]};
+                    Rot rot1;
+                    const double t = dadd(m[0], m[3]);
+                    const double d = dsub(m[2], m[1]);
+                    if (fabs(d) < DBL_MIN) {
+                        rot1.s = 0.0;
+                        rot1.c = 1.0;
+                    } else {
+                        const double u = ddiv(t, d);
+                        const double tmp = dsqrt(dadd(1.0, dmul(u, u)));
+                        rot1.s = ddiv(1.0, tmp);
+                        rot1.c = ddiv(u, tmp);
+                    }
+                    rot_apply(&m[0], &m[2], 2, 1, rot1);
+                    const Rot jr = make_jacobi(m[0], m[1], m[3]);
+                    Rot jl;  // rot1 * jr.transpose()
+                    jl.c = dsub(dmul(rot1.c, jr.c), dmul(rot1.s, -jr.s));
+                    jl.s = dadd(dmul(rot1.c, -jr.s), dmul(rot1.s, jr.c));
+                    rot_apply(&W[3 * p], &W[3 * q], 3, 1, jl);
+                    rot_apply(&U[p], &U[q], 3, 3, jl);
+                    Rot jrt;
+                    jrt.c = jr.c;
+                    jrt.s = -jr.s;
+                    rot_apply(&W[p], &W[q], 3, 3, jrt);
+                    rot_apply(&V[p], &V[q], 3, 3, jrt);
+                    const double a = fabs(W[3 * p + p]), b = fabs(W[3 * q + q]);
+                    const double mx = a < b ? b : a;
+                    max_diag = max_diag < mx ? mx : max_diag;
+                }
+            }
+    }
+    for (int i = 0; i < 3; ++i) {
+        const double a = W[3 * i + i];
+        S[i] = fabs(a);
+        if (a < 0.0)
+            for (int r = 0; r < 3; ++r) U[3 * r + i] = -U[3 * r + i];
+    }
+    for (int i = 0; i < 3; ++i) S[i] = dmul(S[i], scale);
+    for (int i = 0; i < 3; ++i) {
+        int pos = 0;
+        double mx = S[i];
+        for (int k = i + 1; k < 3; ++k)
+            if (S[k] > mx) {
+                mx = S[k];
+                pos = k - i;
+            }
+        if (mx == 0.0) break;
+        if (pos) {
+            pos += i;
+            double tmp = S[i]; S[i] = S[pos]; S[pos] = tmp;
+            for (int r = 0; r < 3; ++r) {
+                tmp = U[3 * r + i]; U[3 * r + i] = U[3 * r + pos]; U[3 * r + pos] = tmp;
+                tmp = V[3 * r + i]; V[3 * r + i] = V[3 * r + pos]; V[3 * r + pos] = tmp;
+            }
+        }
+    }
+}
+
+// length-3 inner product in the order the reference build evaluates it: rows 0-1 of a fixed-size product
+// accumulate left to right (SSE2 packet path), row 2 goes through the unrolled reduction a0 + (a1 + a2)
+__device__ __forceinline__ double dot3_row(int row, double a0, double b0, double a1, double b1, double a2, double b2) {
+    if (row < 2) return dadd(dadd(dmul(a0, b0), dmul(a1, b1)), dmul(a2, b2));
+    return dadd(dmul(a0, b0), dadd(dmul(a1, b1), dmul(a2, b2)));
+}
+
+// icpengine.cpp:93-112: R = V U^T ; det < 0 -> negate V's last column ; t = cB - R cA ; T row-major
+__device__ void solve_from_H(const double* H, const double* cA, const double* cB, double* T, double* Uo, double* So,
+                             double* Vo) {
+    double U[9], S[3], V[9], R[9];
+    svd3(H, U, S, V);
+    if (Uo)
+        for (int i = 0; i < 9; ++i) {
+            Uo[i] = U[i];
+            Vo[i] = V[i];
+        }
+    if (So)
+        for (int i = 0; i < 3; ++i) So[i] = S[i];
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                R[3 * i + j] = dot3_row(i, V[3 * i], U[3 * j], V[3 * i + 1], U[3 * j + 1], V[3 * i + 2], U[3 * j + 2]);
+        if (pass == 1) break;
+        const double det = dadd(dsub(dmul(R[0], dsub(dmul(R[4], R[8]), dmul(R[5], R[7]))),
+                                     dmul(R[1], dsub(dmul(R[3], R[8]), dmul(R[5], R[6])))),
+                                dmul(R[2], dsub(dmul(R[3], R[7]), dmul(R[4], R[6]))));
+        if (!(det < 0.0)) break;
+        for (int r = 0; r < 3; ++r) V[3 * r + 2] = dmul(V[3 * r + 2], -1.0);
+    }
+    for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) T[4 * i + j] = R[3 * i + j];
+        T[4 * i + 3] = dsub(cB[i], dot3_row(i, R[3 * i], cA[0], R[3 * i + 1], cA[1], R[3 * i + 2], cA[2]));
+    }
+}
+
+__device__ __forceinline__ void mat4_mul(const double* A, const double* B, double* C) {  // icpengine.cpp:342
+    double out[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            out[4 * i + j] = dadd(dadd(dadd(dmul(A[4 * i], B[j]), dmul(A[4 * i + 1], B[4 + j])), dmul(A[4 * i + 2], B[8 + j])),
+                                  dmul(A[4 * i + 3], B[12 + j]));
+    for (int i = 0; i < 16; ++i) C[i] = out[i];
+}
+
+// centroids and H from pivoted sums: cA = pa + sa/n ; H = sab - sa sb^T / n
+__device__ __forceinline__ void moments_to_H(const double* b17, const double* pa, const double* pb, double* cA, double* cB,
+                                             double* H) {
+    const double n = b17[0];
+    double ma[3], mb[3];
+    for (int r = 0; r < 3; ++r) {
+        ma[r] = b17[2 + r] / n;
+        mb[r] = b17[5 + r] / n;
+        cA[r] = pa[r] + ma[r];
+        cB[r] = pb[r] + mb[r];
+    }
+    for (int r = 0; r < 3; ++r)
+        for (int q = 0; q < 3; ++q) H[3 * r + q] = b17[8 + 3 * r + q] - b17[2 + r] * mb[q];
+}
+
+// Sums the rank partials in rank order, then RMSE, loop control and the Kabsch solve.
+__global__ void solve_kernel(LoopState* __restrict__ st, const double* __restrict__ rank_parts, int n_ranks,
+                             IterRecord* __restrict__ rec) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double b[STATB_DOUBLES];
+    for (int k = 0; k < STATB_DOUBLES; ++k) {
+        double v = rank_parts[k];
+        for (int r = 1; r < n_ranks; ++r) v += rank_parts[(int64_t)r * STATB_DOUBLES + k];
+        b[k] = v;
+    }
+    const double valid = b[0];
+    const double rmse = valid > 0.0 ? dsqrt(ddiv(b[1], valid)) : 0.0;  // icpengine.cpp:274
+    st->rmse = rmse;
+    int exit_code = 0;
+    const double improvement = dsub(st->prev_error, rmse);  // :288
+    if (fabs(improvement) < st->tolerance) {
+        st->no_improve++;
+        if (st->no_improve >= 3) exit_code = 1;  // converged (:291-305)
+    } else {
+        st->no_improve = 0;
+    }
+    if (exit_code == 0 && rmse > dmul(st->prev_error, 1.1)) exit_code = 2;  // diverged (:311-314)
+    if (exit_code == 0) {
+        st->prev_error = rmse;                    // :316
+        if (valid < 3.0) exit_code = 3;           // :319-323
+    }
+    st->have_T = 0;
+    if (exit_code == 0) {
+        double cA[3], cB[3], H[9], T[16];
+        moments_to_H(b, st->pivot_a, st->pivot_b, cA, cB, H);
+        solve_from_H(H, cA, cB, T, nullptr, nullptr, nullptr);
+        double Tc[16];
+        mat4_mul(T, st->T_cum, Tc);
+        for (int i = 0; i < 16; ++i) {
+            st->T_cum[i] = Tc[i];
+            st->T_last[i] = T[i];
+            st->T_pending[i] = T[i];
+        }
+        st->have_T = 1;
+        // after the move the inlier centroid of the source coincides with cB: pivot both sides there
+        for (int r = 0; r < 3; ++r) {
+            st->pivot_a[r] = cB[r];
+            st->pivot_b[r] = cB[r];
+        }
+    }
+    st->exit_code = exit_code;
+    rec->iteration = st->iter + 1;
+    rec->valid_points = (int)valid;
+    rec->outlier_points = (int)((double)st->n_global - valid);
+    rec->exit_code = exit_code;
+    rec->rmse = rmse;
+    rec->mean = st->mean;
+    rec->std_dev = st->std_dev;
+    rec->threshold = st->threshold;
+    rec->dmin = st->a.dmin;
+    rec->dmax = st->a.dmax;
+    rec->problems = st->a.problems;
+    for (int i = 0; i < 16; ++i) {
+        rec->T_cum[i] = st->T_cum[i];
+        rec->T_last[i] = st->T_last[i];
+    }
+    __threadfence_system();
+}
+
+int solve_launch(Ctx* c, const double* rank_parts, int n_ranks) {
+    solve_kernel<<<1, 32, 0, c->stream>>>(c->d_state, rank_parts, n_ranks, c->d_rec);
+    c->launches++;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+// stage API: best-fit transform from summed moments / from a caller-supplied H
+__global__ void bestfit_kernel(const double* __restrict__ b17, const double* __restrict__ a0, const double* __restrict__ b0,
+                               double* __restrict__ T_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double pa[3] = {a0[0], a0[1], a0[2]}, pb[3] = {b0[0], b0[1], b0[2]};
+    double cA[3], cB[3], H[9], T[16];
+    moments_to_H(b17, pa, pb, cA, cB, H);
+    solve_from_H(H, cA, cB, T, nullptr, nullptr, nullptr);
+    for (int i = 0; i < 16; ++i) T_out[i] = T[i];
+}
+
+__global__ void solve_from_H_kernel(const double* __restrict__ in /* H9, cA3, cB3 */, double* __restrict__ out /* T16,U9,S3,V9 */) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double T[16], U[9], S[3], V[9];
+    solve_from_H(in, in + 9, in + 12, T, U, S, V);
+    for (int i = 0; i < 16; ++i) out[i] = T[i];
+    for (int i = 0; i < 9; ++i) {
+        out[16 + i] = U[i];
+        out[28 + i] = V[i];
+    }
+    for (int i = 0; i < 3; ++i) out[25 + i] = S[i];
+}
+
+int bestfit_launch(Ctx* c, const double* b17, const double* a0, const double* b0, double* T_out) {
+    bestfit_kernel<<<1, 32, 0, c->stream>>>(b17, a0, b0, T_out);
+    c->launches++;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+int solve_from_H_launch(Ctx* c, const double* in15, double* out37) {
+    solve_from_H_kernel<<<1, 32, 0, c->stream>>>(in15, out37);
+    c->launches++;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply / layout kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void apply_T(const double* T, double& x, double& y, double& z) {
+    const double a = x, b = y, c = z;
+    x = dadd(dadd(dadd(dmul(T[0], a), dmul(T[1], b)), dmul(T[2], c)), T[3]);
+    y = dadd(dadd(dadd(dmul(T[4], a), dmul(T[5], b)), dmul(T[6], c)), T[7]);
+    z = dadd(dadd(dadd(dmul(T[8], a), dmul(T[9], b)), dmul(T[10], c)), T[11]);
+}
+
+// applies state->T_pending if state->have_T (used once at loop exit)
+__global__ void __launch_bounds__(256) apply_pending_kernel(const LoopState* __restrict__ st, double* __restrict__ x,
+                                                            double* __restrict__ y, double* __restrict__ z, int64_t n) {
+    if (!st->have_T) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a = x[i], b = y[i], c = z[i];
+    apply_T(st->T_pending, a, b, c);
+    x[i] = a;
+    y[i] = b;
+    z[i] = c;
+}
+
+__global__ void clear_pending_kernel(LoopState* st) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) st->have_T = 0;
+}
+
+__global__ void __launch_bounds__(256) apply_aos_kernel(const double* __restrict__ T, double* __restrict__ xyz, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a = xyz[3 * i], b = xyz[3 * i + 1], c = xyz[3 * i + 2];
+    apply_T(T, a, b, c);
+    xyz[3 * i] = a;
+    xyz[3 * i + 1] = b;
+    xyz[3 * i + 2] = c;
+}
+
+__global__ void __launch_bounds__(256) unsort_kernel(const double* __restrict__ sx, const double* __restrict__ sy,
+                                                     const double* __restrict__ sz, const uint32_t* __restrict__ perm,
+                                                     int64_t n, double* __restrict__ out_xyz) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t j = perm ? (int64_t)perm[i] : i;
+    out_xyz[3 * j] = sx[i];
+    out_xyz[3 * j + 1] = sy[i];
+    out_xyz[3 * j + 2] = sz[i];
+}
+
+// scatter per-query results back to the caller's order: idx (original target index) and distance
+__global__ void __launch_bounds__(256) unsort_results_kernel(const uint32_t* __restrict__ pos, const double* __restrict__ dist,
+                                                             const uint32_t* __restrict__ perm, const TPoint* __restrict__ pts,
+                                                             int64_t n, int32_t* __restrict__ idx_out, double* __restrict__ dist_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t j = perm ? (int64_t)perm[i] : i;
+    idx_out[j] = (int32_t)pts[pos[i]].idx;
+    if (dist_out) dist_out[j] = dist[i];
+}
+
+__global__ void __launch_bounds__(256) aos_to_soa_kernel(const double* __restrict__ xyz, int64_t n, double* __restrict__ sx,
+                                                         double* __restrict__ sy, double* __restrict__ sz) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sx[i] = xyz[3 * i];
+    sy[i] = xyz[3 * i + 1];
+    sz[i] = xyz[3 * i + 2];
+}
+
+static inline int nblk(int64_t n) { return (int)((n + 255) / 256); }
+
+int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n) {
+    apply_pending_kernel<<<nblk(n), 256, 0, c->stream>>>(c->d_state, x, y, z, n);
+    clear_pending_kernel<<<1, 32, 0, c->stream>>>(c->d_state);
+    c->launches += 2;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+int apply_aos_launch(Ctx* c, const double* d_T16, double* xyz, int64_t n) {
+    apply_aos_kernel<<<nblk(n), 256, 0, c->stream>>>(d_T16, xyz, n);
+    c->launches++;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+int unsort_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const uint32_t* perm, int64_t n,
+                  double* out_xyz) {
+    unsort_kernel<<<nblk(n), 256, 0, c->stream>>>(sx, sy, sz, perm, n, out_xyz);
+    c->launches++;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+int unsort_results_launch(Ctx* c, const uint32_t* pos, const double* dist, const uint32_t* perm, int64_t n, int32_t* idx_out,
+                          double* dist_out) {
+    unsort_results_kernel<<<nblk(n), 256, 0, c->stream>>>(pos, dist, perm, c->tree.pts, n, idx_out, dist_out);
+    c->launches++;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+int aos_to_soa_launch(Ctx* c, const double* xyz, int64_t n, double* sx, double* sy, double* sz) {
+    aos_to_soa_kernel<<<nblk(n), 256, 0, c->stream>>>(xyz, n, sx, sy, sz);
+    c->launches++;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+}  // namespace icpb

@@ -1,0 +1,384 @@
+// Exact nearest-neighbour query, one source point per thread (replaces Octree::findNearest /
+// Octree::searchNearest, PointCloudRegistration/core/octree.cpp:128-184, and the per-point loop of
+// core/icpengine.cpp:172-184; CLI twin icp_registration.cpp:108-151,197-205).
+//
+// The answer of the reference is defined by its traversal: depth-first, children ordered by the ROOTED box
+// distance (ties keep octant order), a node skipped when fl(fl(sqrt(s))^2) >= best, points accepted on a
+// strict <.  This kernel executes exactly that traversal with an explicit per-thread stack in shared memory
+// (`dfs`), so indices agree bit-for-bit including every tie.
+//
+// Two provably result-preserving accelerations are layered on top (DESIGN.md "NN query"):
+//   * seeding    -- the traversal is started with best = hi, a hair above the squared distance S of a real
+//                   target point (found by point location, or last iteration's match).  While nothing has
+//                   been accepted yet, any quantity compared against `best` that falls into the guard band
+//                   [hi, hi2] marks the query ambiguous and it is redone unseeded; otherwise the seeded and
+//                   the unseeded traversals make the same accept/prune decisions from the first accepted
+//                   point on, hence return the same index.
+//   * subtree    -- if the query lies inside node A's box with clearance c, c^2 > hi3 > hi2, every node
+//     start         outside A's subtree has box distance above the band and would be pruned whenever it is
+//                   reached, so the traversal may start at A instead of the root.
+#include "internal.h"
+
+namespace icpb {
+
+constexpr int NN_THREADS = 128;
+constexpr int NN_MAX_LEVELS = 22;           // octree_max_depth <= 21  => at most 22 levels on a path
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr int SEED_SCAN = 8;                // points inspected to seed a query
+
+struct NNArgs {
+    const Node* __restrict__ nodes;
+    const TPoint* __restrict__ pts;
+    const double* sx;
+    const double* sy;
+    const double* sz;
+    double* ox;
+    double* oy;
+    double* oz;
+    long long n;
+    uint32_t* pos_out;
+    double* dist_out;
+    const uint32_t* prev_pos;  // last iteration's match per query (may be null)
+    StatA* part_a;
+    const LoopState* state;
+    int apply_pending;
+    int mode;                  // 0: literal traversal from the root; 1: seeded + subtree start
+    double init_best;
+    uint32_t pos_of_idx0;
+};
+
+struct NodeRegs {
+    double lo[3], hi[3];
+    uint32_t child0, pt0, npts, meta;
+};
+
+__device__ __forceinline__ NodeRegs load_node(const Node* __restrict__ nodes, uint32_t i) {
+    const int4* p = reinterpret_cast<const int4*>(nodes + i);
+    int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    NodeRegs r;
+    r.lo[0] = __hiloint2double(a.y, a.x);
+    r.lo[1] = __hiloint2double(a.w, a.z);
+    r.lo[2] = __hiloint2double(b.y, b.x);
+    r.hi[0] = __hiloint2double(b.w, b.z);
+    r.hi[1] = __hiloint2double(c.y, c.x);
+    r.hi[2] = __hiloint2double(c.w, c.z);
+    r.child0 = (uint32_t)d.x;
+    r.pt0 = (uint32_t)d.y;
+    r.npts = (uint32_t)d.z;
+    r.meta = (uint32_t)d.w;
+    return r;
+}
+
+__device__ __forceinline__ void load_point(const TPoint* __restrict__ pts, uint32_t i, double& x, double& y, double& z,
+                                           uint32_t& idx) {
+    const int4* p = reinterpret_cast<const int4*>(pts + i);
+    int4 a = __ldg(p), b = __ldg(p + 1);
+    x = __hiloint2double(a.y, a.x);
+    y = __hiloint2double(a.w, a.z);
+    z = __hiloint2double(b.y, b.x);
+    idx = (uint32_t)b.z;
+}
+
+// OctreeNode::minDistanceTo's per-axis term: max(0, max(lo - q, q - hi))   (octree.cpp:34-36)
+__device__ __forceinline__ double axis_dist(double lo, double hi, double q) {
+    return stdmax(0.0, stdmax(dsub(lo, q), dsub(q, hi)));
+}
+
+struct Search {
+    double best;       // best squared distance so far
+    uint32_t pos;      // its position in the sorted target, NONE while nothing accepted
+    uint32_t idx;      // its original index
+    bool ambiguous;    // a compared quantity fell into the guard band before the first acceptance
+};
+
+// The reference traversal from node `start` (whose own prune test the caller has already made).
+// track: guard-band bookkeeping for seeded runs.  stk: this thread's column of the shared stack.
+template <bool TRACK>
+__device__ __forceinline__ void dfs(const Node* __restrict__ nodes, const TPoint* __restrict__ pts, const double qx,
+                                    const double qy, const double qz, uint32_t start, Search& S, const double band_lo,
+                                    const double band_hi, uint2* stk /* stride NN_THREADS */) {
+    int sp = 0;
+    uint32_t cur = start;
+    bool have_cur = true;
+    for (;;) {
+        if (have_cur) {
+            const NodeRegs nd = load_node(nodes, cur);
+            const uint32_t mask = nd.meta & 0xFFu;
+            if (mask == 0) {
+                // leaf: octree.cpp:139-150.  The reference scans ascending original index with a strict <,
+                // i.e. within one leaf the smallest distance wins and equal distances go to the lowest index;
+                // points here are in key order, so that rule is applied explicitly.
+                bool from_this_leaf = false;
+                for (uint32_t k = 0; k < nd.npts; ++k) {
+                    double px, py, pz;
+                    uint32_t pidx;
+                    load_point(pts, nd.pt0 + k, px, py, pz, pidx);
+                    const double d2 = sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz));
+                    if (TRACK && S.pos == NONE && d2 >= band_lo && d2 <= band_hi) S.ambiguous = true;
+                    if (d2 < S.best || (from_this_leaf && d2 == S.best && pidx < S.idx)) {
+                        S.best = d2;
+                        S.pos = nd.pt0 + k;
+                        S.idx = pidx;
+                        from_this_leaf = true;
+                    }
+                }
+                have_cur = false;
+            } else {
+                // inner node: octree.cpp:152-171
+                double dl[3], dh[3];
+                const double q[3] = {qx, qy, qz};
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const double mid = dmul(dadd(nd.lo[a], nd.hi[a]), 0.5);
+                    const double l = axis_dist(nd.lo[a], mid, q[a]);
+                    const double h = axis_dist(mid, nd.hi[a], q[a]);
+                    dl[a] = dmul(l, l);
+                    dh[a] = dmul(h, h);
+                }
+                double md[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    const double s = dadd(dadd((o & 1) ? dh[0] : dl[0], (o & 2) ? dh[1] : dl[1]), (o & 4) ? dh[2] : dl[2]);
+                    md[o] = ((mask >> o) & 1u) ? dsqrt(s) : __longlong_as_double(0x7FF0000000000000LL);
+                }
+                // rank = position after a stable ascending sort by md (std::sort on <= 8 items == insertion sort)
+                uint32_t word = 0;
+                double mdmin = md[0];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t r = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < i) r += (md[j] <= md[i]) ? 1u : 0u;
+                        if (j > i) r += (md[j] < md[i]) ? 1u : 0u;
+                    }
+                    word |= (uint32_t)i << (3 * r);
+                    if (i > 0) mdmin = fmin(mdmin, md[i]);
+                }
+                const uint32_t cnt = __popc(mask);
+                const double m0 = dmul(mdmin, mdmin);
+                if (TRACK && S.pos == NONE && m0 >= band_lo && m0 <= band_hi) S.ambiguous = true;
+                if (m0 >= S.best) {
+                    have_cur = false;  // nearest child pruned => all children pruned (octree.cpp:134-135)
+                } else {
+                    const uint32_t oct = word & 7u;
+                    if (cnt > 1) {
+                        // entry: x = node, y = order word (24 bits) | next position (4 bits) | count (4 bits)
+                        stk[sp * NN_THREADS] = make_uint2(cur, (word & 0xFFFFFFu) | (1u << 24) | (cnt << 28));
+                        ++sp;
+                    }
+                    cur = nd.child0 + __popc(mask & ((1u << oct) - 1u));
+                }
+            }
+        } else {
+            if (sp == 0) break;
+            uint2 top = stk[(sp - 1) * NN_THREADS];
+            const uint32_t k = (top.y >> 24) & 0xFu, cnt = top.y >> 28;
+            const uint32_t oct = (top.y >> (3 * k)) & 7u;
+            const NodeRegs pn = load_node(nodes, top.x);
+            const double q[3] = {qx, qy, qz};
+            double d[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double mid = dmul(dadd(pn.lo[a], pn.hi[a]), 0.5);
+                const bool up = (oct >> a) & 1u;
+                d[a] = axis_dist(up ? mid : pn.lo[a], up ? pn.hi[a] : mid, q[a]);
+            }
+            const double mdc = dsqrt(sumsq3(d[0], d[1], d[2]));
+            const double m = dmul(mdc, mdc);
+            if (TRACK && S.pos == NONE && m >= band_lo && m <= band_hi) S.ambiguous = true;
+            if (m >= S.best) {
+                --sp;  // this sibling and every later one (larger distance) are pruned
+                continue;
+            }
+            if (k + 1 >= cnt) {
+                --sp;
+            } else {
+                top.y = (top.y & ~(0xFu << 24)) | ((k + 1) << 24);
+                stk[(sp - 1) * NN_THREADS] = top;
+            }
+            const uint32_t mask = pn.meta & 0xFFu;
+            cur = pn.child0 + __popc(mask & ((1u << oct) - 1u));
+            have_cur = true;
+        }
+    }
+}
+
+__device__ __forceinline__ StatA warp_merge(StatA v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        StatA w;
+        w.n = __shfl_xor_sync(0xffffffffu, v.n, o);
+        w.mean = __shfl_xor_sync(0xffffffffu, v.mean, o);
+        w.m2 = __shfl_xor_sync(0xffffffffu, v.m2, o);
+        w.dmin = __shfl_xor_sync(0xffffffffu, v.dmin, o);
+        w.dmax = __shfl_xor_sync(0xffffffffu, v.dmax, o);
+        w.problems = __shfl_xor_sync(0xffffffffu, v.problems, o);
+        // merge in a lane-independent order so every lane ends with the same bits
+        const bool lower = (threadIdx.x & o) == 0;
+        v = lower ? stat_merge(v, w) : stat_merge(w, v);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
+    __shared__ uint2 stack[NN_MAX_LEVELS * NN_THREADS];
+    __shared__ StatA warp_part[NN_THREADS / 32];
+    const long long i = (long long)blockIdx.x * NN_THREADS + threadIdx.x;
+    const bool active = i < A.n;
+    uint2* stk = stack + threadIdx.x;
+
+    StatA st;
+    st.n = 0.0; st.mean = 0.0; st.m2 = 0.0; st.dmin = DBL_MAX; st.dmax = 0.0; st.problems = 0.0;
+
+    if (active) {
+        double qx = A.sx[i], qy = A.sy[i], qz = A.sz[i];
+        if (A.apply_pending && A.state->have_T) {
+            // src = T * src (icpengine.cpp:345): ((T0 x + T1 y) + T2 z) + T3 * 1.0, no contraction
+            const double* T = A.state->T_pending;
+            const double x = qx, y = qy, z = qz;
+            qx = dadd(dadd(dadd(dmul(T[0], x), dmul(T[1], y)), dmul(T[2], z)), T[3]);
+            qy = dadd(dadd(dadd(dmul(T[4], x), dmul(T[5], y)), dmul(T[6], z)), T[7]);
+            qz = dadd(dadd(dadd(dmul(T[8], x), dmul(T[9], y)), dmul(T[10], z)), T[11]);
+            A.ox[i] = qx;
+            A.oy[i] = qy;
+            A.oz[i] = qz;
+        }
+        Search S;
+        S.best = A.init_best;
+        S.pos = NONE;
+        S.idx = 0;
+        S.ambiguous = false;
+        const bool finite_q = isfinite(qx) && isfinite(qy) && isfinite(qz);
+        bool need_full = finite_q;
+        if (A.mode == 1 && finite_q) {
+            // ---- point location: walk down the cell path of q, remembering each level's clearance ----
+            uint32_t n = 0;
+            int level = 0;
+            NodeRegs nd;
+            // Running pointer rather than stk[level * NN_THREADS]: ptxas 12.9 (sm_100a) mis-addressed the indexed
+            // form of this store by two rows in the rotated loop (seen in SASS and on the device), PTX was correct.
+            uint2* path = stk;
+            for (;;) {
+                nd = load_node(A.nodes, n);
+                double c = fmin(fmin(dsub(qx, nd.lo[0]), dsub(nd.hi[0], qx)),
+                                fmin(fmin(dsub(qy, nd.lo[1]), dsub(nd.hi[1], qy)), fmin(dsub(qz, nd.lo[2]), dsub(nd.hi[2], qz))));
+                float cf = (c > 0.0) ? __double2float_rd(c) : 0.0f;
+                *path = make_uint2(n, __float_as_uint(cf));
+                const uint32_t mask = nd.meta & 0xFFu;
+                if (mask == 0) break;
+                uint32_t oct = 0;
+                oct |= (qx > dmul(dadd(nd.lo[0], nd.hi[0]), 0.5)) ? 1u : 0u;
+                oct |= (qy > dmul(dadd(nd.lo[1], nd.hi[1]), 0.5)) ? 2u : 0u;
+                oct |= (qz > dmul(dadd(nd.lo[2], nd.hi[2]), 0.5)) ? 4u : 0u;
+                if (!((mask >> oct) & 1u)) break;
+                n = nd.child0 + __popc(mask & ((1u << oct) - 1u));
+                ++level;
+                path += NN_THREADS;
+            }
+            // ---- seed: squared distance of a real target point ----
+            double Sd = __longlong_as_double(0x7FF0000000000000LL);
+            const uint32_t ns = nd.npts < (uint32_t)SEED_SCAN ? nd.npts : (uint32_t)SEED_SCAN;
+            for (uint32_t k = 0; k < ns; ++k) {
+                double px, py, pz;
+                uint32_t pidx;
+                load_point(A.pts, nd.pt0 + k, px, py, pz, pidx);
+                Sd = fmin(Sd, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)));
+            }
+            if (A.prev_pos) {
+                const uint32_t pp = A.prev_pos[i];
+                if (pp != NONE) {
+                    double px, py, pz;
+                    uint32_t pidx;
+                    load_point(A.pts, pp, px, py, pz, pidx);
+                    Sd = fmin(Sd, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)));
+                }
+            }
+            const double eps = 9.094947017729282e-13;  // 2^-40
+            const double hi = dadd(dmul(Sd, 1.0 + eps), 1e-300);
+            const double hi2 = dmul(hi, 1.0 + eps);
+            const double hi3 = dmul(hi2, 1.0 + eps);
+            if (hi3 < A.init_best) {  // also false for inf/NaN
+                // ---- subtree start: deepest path node whose clearance^2 clears the band ----
+                uint32_t start = 0;
+                for (int l = level; l > 0; --l) {
+                    const uint2 e = stk[l * NN_THREADS];
+                    const double cf = (double)__uint_as_float(e.y);
+                    if (cf * cf > hi3) {
+                        start = e.x;
+                        break;
+                    }
+                }
+                S.best = hi;
+                dfs<true>(A.nodes, A.pts, qx, qy, qz, start, S, hi, hi2, stk);
+                need_full = S.ambiguous || S.pos == NONE;
+            }
+        }
+        if (need_full) {
+            // ---- the reference traversal from the root (octree.cpp:175-184) ----
+            S.best = A.init_best;
+            S.pos = NONE;
+            S.idx = 0;
+            S.ambiguous = false;
+            const NodeRegs root = load_node(A.nodes, 0);
+            const double mdr = dsqrt(sumsq3(axis_dist(root.lo[0], root.hi[0], qx), axis_dist(root.lo[1], root.hi[1], qy),
+                                            axis_dist(root.lo[2], root.hi[2], qz)));
+            if (!(dmul(mdr, mdr) >= S.best)) dfs<false>(A.nodes, A.pts, qx, qy, qz, 0u, S, 0.0, 0.0, stk);
+        }
+        // findNearest returns index 0 when nothing was accepted (best_idx = 0 initially, octree.cpp:179)
+        const uint32_t pos = (S.pos == NONE) ? A.pos_of_idx0 : S.pos;
+        double px, py, pz;
+        uint32_t pidx;
+        load_point(A.pts, pos, px, py, pz, pidx);
+        // computeDistance(p_src, p_tgt) (icpengine.cpp:68-74)
+        const double d = dsqrt(sumsq3(dsub(qx, px), dsub(qy, py), dsub(qz, pz)));
+        A.pos_out[i] = pos;
+        A.dist_out[i] = d;
+        st.n = 1.0;
+        st.mean = d;
+        if (isfinite(d)) {
+            st.dmin = d;
+            st.dmax = d;
+        } else {
+            st.problems = 1.0;
+        }
+    }
+    if (A.part_a) {
+        st = warp_merge(st);
+        if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = st;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            StatA r = warp_part[0];
+#pragma unroll
+            for (int w = 1; w < NN_THREADS / 32; ++w) r = stat_merge(r, warp_part[w]);
+            A.part_a[blockIdx.x] = r;
+        }
+    }
+}
+
+int nn_grid_blocks(int64_t n) { return (int)((n + NN_THREADS - 1) / NN_THREADS); }
+
+int nn_launch(Ctx* c, const NNLaunch& L) {
+    if (L.n <= 0) return ICP_OK;
+    NNArgs A;
+    A.nodes = c->tree.nodes;
+    A.pts = c->tree.pts;
+    A.sx = L.sx; A.sy = L.sy; A.sz = L.sz;
+    A.ox = L.ox; A.oy = L.oy; A.oz = L.oz;
+    A.n = L.n;
+    A.pos_out = L.pos_out;
+    A.dist_out = L.dist_out;
+    A.prev_pos = L.prev_pos;
+    A.part_a = L.part_a;
+    A.state = L.state;
+    A.apply_pending = L.apply_pending;
+    A.mode = L.mode;
+    A.init_best = L.init_best;
+    A.pos_of_idx0 = c->tree.pos_of_idx0;
+    nn_kernel<<<nn_grid_blocks(L.n), NN_THREADS, 0, c->stream>>>(A);
+    c->launches++;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+}  // namespace icpb

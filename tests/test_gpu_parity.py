@@ -1,0 +1,340 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+
+Bars: tree structure, NN indices, distances, inlier masks, SVD given H and transform apply
+are BIT-EXACT; statistics that involve a sum over N agree to 1e-12 relative (the reference sums sequentially,
+the GPU in a fixed tree order); end-to-end runs have identical iteration counts and T within 1e-9.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import clouds
+from iterativeclosestpoint_b200 import synth
+from iterativeclosestpoint_b200.engine import (ICP, Handle, ICPEngine, ICPParameters, Octree, VARIANT_CLI,
+                                               VARIANT_ENGINE, best_fit_transform)
+
+pytestmark = pytest.mark.gpu
+
+REL_SUM = 1e-12   # tolerance for quantities that contain a length-N floating-point sum
+REL_E2E = 1e-9    # north_star: final transform within 1e-9 relative
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(1e-300, float(np.max(np.abs(b)))))
+
+
+TREE_CASES = [
+    ("terrain20k", lambda: clouds.terrain(20000), 10, 20),
+    ("terrain_las", lambda: clouds.terrain(8000, las=True), 10, 20),
+    ("terrain_leaf5_depth6", lambda: clouds.terrain(8000), 5, 6),
+    ("terrain_leaf100", lambda: clouds.terrain(8000), 100, 21),
+    ("duplicates", clouds.duplicates, 10, 20),
+    ("coincident", clouds.coincident, 10, 20),
+    ("two_clusters", clouds.two_clusters, 10, 20),
+    ("planar", clouds.planar, 10, 20),
+    ("collinear", clouds.collinear, 10, 20),
+    ("lattice", clouds.lattice, 10, 20),
+    ("lattice_exact", clouds.lattice_exact, 10, 20),
+    ("single", lambda: np.array([[1.0, 2.0, 3.0]]), 10, 20),
+    ("eleven", lambda: clouds.terrain(11), 10, 20),
+    ("depth0", lambda: clouds.terrain(500), 10, 0),
+]
+
+
+@pytest.mark.parametrize("name,make,leaf,depth", TREE_CASES, ids=[c[0] for c in TREE_CASES])
+def test_octree_structure_bit_exact(handle, oracle, name, make, leaf, depth):
+    tgt = make()
+    handle.octree_build(tgt, leaf, depth)
+    got = handle.octree_dump()
+    want = oracle.octree(tgt, leaf, depth).dump()
+    for k in ("depth", "key", "leaf", "count", "idx"):
+        assert np.array_equal(got[k], want[k]), f"{name}: node table field {k} differs"
+    assert np.array_equal(got["box"], want["box"]), f"{name}: boxes differ (must be bit-identical bisections)"
+    info = handle.octree_info()
+    assert info.n_nodes == len(want["depth"]) and info.n_leaves == int(want["leaf"].sum())
+    assert info.depth == int(want["depth"].max())
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["literal", "seeded"])
+@pytest.mark.parametrize("name,make,leaf,depth", TREE_CASES, ids=[c[0] for c in TREE_CASES])
+def test_nn_indices_bit_exact(handle, oracle, name, make, leaf, depth, mode):
+    tgt = make()
+    handle.set_option("nn_mode", mode)
+    handle.octree_build(tgt, leaf, depth)
+    otree = oracle.octree(tgt, leaf, depth)
+    for qname, q in clouds.query_sets(tgt).items():
+        idx, dist, _ = handle.nn_query(q)
+        want = otree.find_nearest(q)
+        bad = np.flatnonzero(idx != want)
+        assert bad.size == 0, f"{name}/{qname}/mode{mode}: {bad.size} of {len(q)} indices differ, first {bad[:5]}"
+        # computeDistance: sqrt(dx*dx+dy*dy+dz*dz) -- numpy evaluates the same expression in the same order
+        dx = q - tgt[want]
+        d = np.sqrt(dx[:, 0] * dx[:, 0] + dx[:, 1] * dx[:, 1] + dx[:, 2] * dx[:, 2])
+        assert np.array_equal(dist, d), f"{name}/{qname}: distances are not bit-identical"
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["literal", "seeded"])
+def test_nn_lattice_ties_follow_reference_traversal_order(handle, oracle, mode):
+    """Exactly equidistant candidates: the winner is the first one the reference's DFS visits, not the lowest index."""
+    lat = clouds.lattice_exact()
+    q = clouds.lattice_tie_queries(lat)
+    handle.set_option("nn_mode", mode)
+    handle.octree_build(lat, 10, 20)
+    idx, _, _ = handle.nn_query(q)
+    want = oracle.octree(lat).find_nearest(q)
+    d2 = ((q[:, None, :] - lat[None, :, :]) ** 2).sum(-1)
+    tied = (d2 == d2.min(1, keepdims=True)).sum(1) > 1
+    assert tied.sum() > 200, "the fixture must contain many exact ties"
+    assert np.array_equal(idx, want)
+    assert (want[tied] != d2.argmin(1)[tied]).sum() > 0, "fixture should include ties NOT won by the lowest index"
+
+
+def test_nn_nonfinite_queries_return_index_zero(handle, oracle):
+    tgt = clouds.terrain(3000)
+    q = np.array([[np.nan, 1.0, 1.0], [np.inf, 0.0, 0.0], [1.0, -np.inf, 2.0], [1e300, 1e300, 1e300], [5.0, 5.0, 1.0]])
+    handle.octree_build(tgt)
+    want = oracle.octree(tgt).find_nearest(q)
+    for mode in (0, 1):
+        handle.set_option("nn_mode", mode)
+        idx, _, _ = handle.nn_query(q)
+        assert np.array_equal(idx, want)
+
+
+def test_nn_cli_variant_initial_best(handle, oracle):
+    """The CLI starts from best = 1e20 instead of DBL_MAX (icp_registration.cpp:201)."""
+    tgt = clouds.terrain(3000)
+    q = np.concatenate([clouds.query_sets(tgt)["stress"][:500], np.array([[3e10, 0.0, 0.0], [1e11, 1e11, 0.0]])])
+    handle.set_params(ICPParameters(), VARIANT_CLI)
+    handle.octree_build(tgt)
+    want = oracle.octree(tgt).find_nearest(q, variant=1)
+    for mode in (0, 1):
+        handle.set_option("nn_mode", mode)
+        idx, _, _ = handle.nn_query(q)
+        assert np.array_equal(idx, want)
+
+
+def test_octree_class_single_query(oracle):
+    tgt = clouds.terrain(2000)
+    t = Octree(tgt, 10, 20)
+    want = oracle.octree(tgt).find_nearest(tgt[:5] + 0.01)
+    assert [t.findNearest(p) for p in tgt[:5] + 0.01] == list(want)
+    assert Octree(np.zeros((0, 3))).findNearest([0, 0, 0]) == 0
+
+
+@pytest.mark.parametrize("variant", [VARIANT_ENGINE, VARIANT_CLI], ids=["engine", "cli"])
+@pytest.mark.parametrize("it", [0, 3])
+def test_iteration_stats_mask_bit_exact(handle, oracle, variant, it):
+    src, tgt = synth.make_pair(30000, 2, "stress")
+    idx = oracle.octree(tgt).find_nearest(src)
+    handle.set_params(ICPParameters(sigmaMultiplier=2.5), variant)
+    handle.octree_build(tgt)
+    dist, mask, st = handle.iteration_stats(src, idx, it)
+    sigma = 3.0 if variant == VARIANT_CLI else 2.5
+    odist, omask, ost = oracle.iteration_stats(src, tgt, idx, it, sigma, variant)
+    assert np.array_equal(dist, odist)
+    assert np.array_equal(mask, omask)
+    assert st.valid_count == ost.valid_count and st.outlier_count == ost.outlier_count
+    for f in ("mean", "std_dev", "threshold", "rmse", "sum_sq"):
+        assert abs(getattr(st, f) - getattr(ost, f)) <= REL_SUM * abs(getattr(ost, f)), f
+    if variant == VARIANT_ENGINE:
+        assert st.min_distance == ost.min_distance and st.max_distance == ost.max_distance
+
+
+def test_iteration_stats_out_of_range_index(handle, oracle):
+    src, tgt = synth.make_pair(5000, 2, "near")
+    idx = oracle.octree(tgt).find_nearest(src)
+    idx[7] = -1
+    idx[11] = len(tgt)
+    handle.octree_build(tgt)
+    dist, mask, st = handle.iteration_stats(src, idx, 1)
+    odist, omask, ost = oracle.iteration_stats(src, tgt, idx, 1, 3.0, 0)
+    assert st.problem_count == ost.problem_count == 2
+    assert dist[7] == odist[7] == np.finfo(np.float64).max
+    assert np.array_equal(mask, omask)
+
+
+def test_solve_from_H_bit_exact(handle, oracle):
+    """The single-thread Jacobi SVD follows Eigen's operation order: identical U, S, V, T for identical H."""
+    r = np.random.default_rng(5)
+    for i in range(300):
+        H = r.normal(size=(3, 3)) * 10 ** r.uniform(-3, 6)
+        if i % 7 == 0:
+            H[:, 2] = H[:, 0] * 2      # rank deficient
+        if i % 11 == 0:
+            H = np.diag(r.normal(size=3))
+        if i % 13 == 0:
+            H = -np.abs(H)             # reflection branch
+        if i == 0:
+            H = np.zeros((3, 3))
+        cA = r.normal(size=3) * 100
+        cB = r.normal(size=3) * 100
+        T, U, S, V = handle.solve_from_H(H, cA, cB)
+        oU, oS, oV = oracle.svd3(H)
+        assert np.array_equal(U, oU) and np.array_equal(S, oS) and np.array_equal(V, oV), i
+        assert np.array_equal(T, oracle.solve_from_H(H, cA, cB)), i
+
+
+def test_best_fit_transform(handle, oracle):
+    r = np.random.default_rng(6)
+    for n, offset in ((3, 0.0), (50, 10.0), (20000, 5e5)):
+        a = r.normal(size=(n, 3)) * 30 + offset
+        R = synth.rotation_zyx(0.3, -0.1, 0.2)
+        b = a @ R.T + np.array([1.0, -2.0, 0.5]) + r.normal(size=(n, 3)) * 0.01
+        T = handle.best_fit_transform(a, b)
+        oT = oracle.kabsch(a, b)
+        assert rel(T[:3, :3], oT[:3, :3]) < 1e-11
+        assert np.max(np.abs(T[:3, 3] - oT[:3, 3])) < 1e-9 * max(1.0, offset)
+        assert np.array_equal(best_fit_transform(a, b, handle=handle), T)
+    # planar / collinear clouds exercise the reflection fix and rank-deficient H
+    for cloud in (clouds.planar(2000), clouds.collinear(300)):
+        b = cloud @ R.T + 1.0
+        T = handle.best_fit_transform(cloud, b)
+        oT = oracle.kabsch(cloud, b)
+        assert np.allclose(T @ T.T[:, :4], T @ T.T[:, :4])
+        assert abs(np.linalg.det(T[:3, :3]) - 1.0) < 1e-9
+        if cloud is not None and np.linalg.matrix_rank(cloud - cloud.mean(0), tol=1e-6) >= 2:
+            assert rel(T, oT) < 1e-8
+
+
+def test_apply_transform_bit_exact(handle, oracle):
+    r = np.random.default_rng(8)
+    T = oracle.solve_from_H(r.normal(size=(3, 3)), [1, 2, 3], [3, 2, 1])
+    x = r.normal(size=(5000, 3)) * 1000 + 4e5
+    assert np.array_equal(handle.apply_transform(T, x), oracle.apply(T, x))
+
+
+def _check_run(got, want, n_src, tol=REL_E2E):
+    assert got.status == want.status
+    assert got.success == want.success
+    assert got.totalIterations == want.total_iterations
+    assert got.loopIterations == want.loop_iterations
+    assert len(got.iterationHistory) == len(want.history)
+    for g, w in zip(got.iterationHistory, want.history):
+        assert g.iteration == w.iteration
+        assert g.validPoints == w.valid_points and g.outlierPoints == w.outlier_points
+        assert abs(g.rmse - w.rmse) <= tol * max(w.rmse, 1e-30)
+        assert rel(g.transform, w.transform) <= tol
+        assert g.hasAngles == w.has_angles
+        if w.has_angles and np.isfinite(w.rotation_angle) and w.rotation_angle > 1e-3:
+            assert abs(g.rotationAngle - w.rotation_angle) <= 1e-6 * w.rotation_angle
+            assert abs(g.translationDistance - w.translation_distance) <= tol * max(1.0, w.translation_distance)
+    assert abs(got.finalRMSE - want.final_rmse) <= tol * max(want.final_rmse, 1e-30)
+    if want.success:
+        assert rel(got.finalR, want.final_R) <= tol
+        assert np.max(np.abs(got.finalT - want.final_t)) <= tol * max(1.0, float(np.max(np.abs(want.final_t))))
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["literal", "seeded"])
+def test_register_config1_engine(handle, oracle, mode):
+    """BASELINE.json config #1: 10k-point cloud vs transformed + noised copy, 50 / 1e-6 / 3 sigma / 10 / 20."""
+    src, tgt = synth.make_test_icp_pair(10000)
+    want = oracle.icp(src, tgt)
+    work = src.copy()
+    handle.set_option("nn_mode", mode)
+    handle.set_params(ICPParameters(), VARIANT_ENGINE)
+    got = handle.register(work, tgt)
+    _check_run(got, want, len(src))
+    assert np.max(np.abs(work - want.source_out)) <= 1e-9 * float(np.max(np.abs(want.source_out)))
+    assert got.timings_ms["loop"] > 0
+
+
+def test_register_trace_masks_and_indices_bit_exact(handle, oracle):
+    """Per iteration on identical inputs: NN indices and inlier masks bit-exact, stats to 1e-12."""
+    src, tgt = synth.make_pair(20000, 2, "primary")
+    want = oracle.icp(src, tgt, max_iterations=6, trace_iters=6)
+    handle.octree_build(tgt)
+    for k in range(want.loop_iterations):
+        cur = want.trace["src_before"][k]
+        idx, dist, _ = handle.nn_query(cur)
+        assert np.array_equal(idx, want.trace["idx"][k]), f"iteration {k}"
+        assert np.array_equal(dist, want.trace["dist"][k])
+        d, mask, st = handle.iteration_stats(cur, idx, k)
+        assert np.array_equal(mask, want.trace["mask"][k]), f"iteration {k}"
+        ost = want.trace["stats"][k]
+        assert abs(st.threshold - ost.threshold) <= REL_SUM * ost.threshold
+        assert abs(st.rmse - ost.rmse) <= REL_SUM * ost.rmse
+
+
+def test_register_cli_variant(handle, oracle):
+    src, tgt = synth.make_test_icp_pair(6000, seed=77)
+    want = oracle.icp(src, tgt, max_iterations=20, tolerance=1e-2, variant=1)
+    work = src.copy()
+    R, t, its = ICP(work, tgt, 20, 1e-2, handle=handle)
+    assert len(its) == len(want.history)
+    assert rel(R, want.final_R) <= REL_E2E and np.max(np.abs(t - want.final_t)) <= REL_E2E
+    for g, w in zip(its, want.history):
+        assert rel(g, w.transform) <= REL_E2E
+    assert np.max(np.abs(work - want.source_out)) <= 1e-9 * float(np.max(np.abs(want.source_out)))
+
+
+def test_engine_class_signals_and_exits(oracle):
+    src, tgt = synth.make_pair(4000, 2, "near")
+    eng = ICPEngine()
+    order = []
+    eng.started.connect(lambda: order.append("s"))
+    eng.iterationCompleted.connect(lambda r: order.append("i"))
+    eng.progressUpdated.connect(lambda i, t, r: order.append("p"))
+    eng.finished.connect(lambda ok, msg: order.append(("f", ok, msg)))
+    eng.setParameters(ICPParameters(maxIterations=30))
+    work = src.copy()
+    eng.registerPointClouds(work, tgt)
+    want = oracle.icp(src, tgt, max_iterations=30)
+    res = eng.getResult()
+    assert res.success and res.totalIterations == want.total_iterations
+    assert order[0] == "s" and order[-1] == ("f", True, "配准成功")
+    assert "".join(o for o in order[1:-1]) == "ip" * want.total_iterations   # icpengine.cpp:364-367 order
+    assert np.max(np.abs(work - want.source_out)) < 1e-9 * np.max(np.abs(work))
+    # cancel from inside the 2nd iterationCompleted: the source must stay untouched (icpengine.cpp:160-164)
+    eng2 = ICPEngine()
+    seen = []
+    eng2.iterationCompleted.connect(lambda r: (seen.append(r.iteration), eng2.stop() if len(seen) == 2 else None))
+    fin = []
+    eng2.finished.connect(lambda ok, msg: fin.append((ok, msg)))
+    work2 = src.copy()
+    eng2.registerPointClouds(work2, tgt)
+    assert fin == [(False, "用户取消")] and len(seen) == 2
+    assert np.array_equal(work2, src) and not eng2.getResult().success
+    # empty / null inputs and < 3 inliers
+    fin.clear(); eng2.registerPointClouds(np.zeros((0, 3)), tgt); assert fin == [(False, "点云数据为空")]
+    fin.clear(); eng2.registerPointClouds(None, tgt); assert fin == [(False, "源点云或目标点云为空")]
+    tiny_s = np.array([[0.0, 0, 0], [1.0, 0, 0]]); tiny_t = np.array([[0, 0, 0.1], [1, 0, 0.1], [0, 1, 0.1]])
+    fin.clear(); keep = tiny_s.copy(); eng2.registerPointClouds(tiny_s, tiny_t)
+    assert fin == [(False, "有效点对不足")] and np.array_equal(tiny_s, keep)
+    assert oracle.icp(keep, tiny_t).status == 3
+
+
+def test_register_divergence_and_max_iterations(handle, oracle):
+    src, tgt = synth.make_pair(5000, 2, "stress")
+    for iters in (1, 4):
+        want = oracle.icp(src, tgt, max_iterations=iters)
+        handle.set_params(ICPParameters(maxIterations=iters))
+        work = src.copy()
+        got = handle.register(work, tgt)
+        _check_run(got, want, len(src))
+        assert np.max(np.abs(work - want.source_out)) <= 1e-9 * float(np.max(np.abs(want.source_out)))
+
+
+def test_full_size_config2_properties(handle, oracle):
+    """BASELINE.json config #2 at full size (1M <-> 1M): index parity on a 50k sample against the oracle, plus
+    size-independent properties on all queries (idempotence, self-match, brute-force distance on a subsample)."""
+    src, tgt = synth.make_pair(1_000_000, 2, "stress")
+    handle.octree_build(tgt)
+    idx, dist, ms = handle.nn_query(src)
+    sample = np.random.default_rng(3).permutation(len(src))[:50000]
+    want = oracle.octree(tgt).find_nearest(src[sample], nthreads=oracle.hw_threads())
+    assert np.array_equal(idx[sample], want)
+    # distances are the true minimum: brute force on 300 queries
+    for i in sample[:300]:
+        assert dist[i] == np.sqrt(((tgt - src[i]) ** 2).sum(1).min()) or abs(
+            dist[i] - np.sqrt(((tgt - src[i]) ** 2).sum(1).min())) < 1e-12
+    # querying the target against itself returns a point at distance 0 (itself or an exact duplicate)
+    sidx, sdist, _ = handle.nn_query(tgt[:200000])
+    assert np.all(sdist == 0.0)
+    assert np.array_equal(tgt[sidx], tgt[:200000])
+    # both traversal modes agree on every query
+    handle.set_option("nn_mode", 0)
+    idx0, dist0, _ = handle.nn_query(src)
+    assert np.array_equal(idx0, idx) and np.array_equal(dist0, dist)
