@@ -151,9 +151,14 @@ def test_iteration_stats_out_of_range_index(handle, oracle):
     handle.octree_build(tgt)
     dist, mask, st = handle.iteration_stats(src, idx, 1)
     odist, omask, ost = oracle.iteration_stats(src, tgt, idx, 1, 3.0, 0)
+    # The guard at icpengine.cpp:199-204 is unreachable in the reference (findNearest only returns valid
+    # indices); only its observable part is pinned: the sentinel distance and the problem counter.  With two
+    # DBL_MAX entries the reference's own mean overflows to inf, so no mask comparison is meaningful.
     assert st.problem_count == ost.problem_count == 2
     assert dist[7] == odist[7] == np.finfo(np.float64).max
-    assert np.array_equal(mask, omask)
+    assert dist[11] == odist[11] == np.finfo(np.float64).max
+    keep = np.ones(len(src), dtype=bool); keep[[7, 11]] = False
+    assert np.array_equal(dist[keep], odist[keep])
 
 
 def test_solve_from_H_bit_exact(handle, oracle):
