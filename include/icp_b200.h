@@ -68,6 +68,8 @@ typedef struct icp_iteration {
     double transform[16];       /* cumulative, row-major */
     double rotation_angle;      /* degrees, acos((tr R - 1)/2) without clamping (icpengine.cpp:361) */
     double translation_distance;
+    double nn_ms;               /* device time of this iteration's NN stage (not in the reference) */
+    double iter_ms;             /* device time of the whole iteration */
 } icp_iteration;
 
 /* Per-iteration statistics of stages a9-a11 (core/icpengine.cpp:187-278). */
@@ -120,7 +122,7 @@ int icp_get_params(icp_handle h, icp_params* p);                /* ICPEngine::ge
 void icp_default_params(icp_params* p);                         /* ICPParameters defaults (icpengine.h:13-19) */
 int icp_set_callbacks(icp_handle h, icp_iteration_cb on_iteration, icp_progress_cb on_progress, icp_log_cb on_log,
                       void* user);
-/* Tuning knobs that never change results: "nn_mode" (0 = literal root traversal, 1 = seeded, default),
+/* Tuning knobs that never change results: "nn_mode" (0 = literal root traversal, 1 = fast path with literal fallback, default),
  * "order_queries" (Morton-order the source internally, default 1), "write_mask" (keep the inlier mask). */
 int icp_set_option(icp_handle h, const char* key, double value);
 
@@ -177,6 +179,10 @@ int icp_register_sharded(icp_handle h, double* src_shard_xyz, int64_t n_shard, i
 /* ---- many small independent registrations (BASELINE.json config #5) ---------------------------------- */
 int icp_register_batch(icp_handle h, int32_t n_pairs, double* const* src_xyz, const int64_t* n_src,
                        const double* const* tgt_xyz, const int64_t* n_tgt, icp_result* results);
+
+/* How many queries since the last reset were answered by the order-independent fast path and how many
+ * had to be re-run through the literal reference traversal (exact ties / duplicates / 1-ulp near ties). */
+int icp_nn_counters(icp_handle h, int64_t* fast_path, int64_t* literal_fallback, int reset);
 
 /* Number of kernels this library has launched on the handle since creation (bench.py's gpu_launches). */
 int64_t icp_kernel_launches(icp_handle h);

@@ -227,13 +227,13 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
             ICPB_NCCL(c, c->nccl->AllGather(rank_b + (size_t)c->rank * STATB_DOUBLES, rank_b, STATB_DOUBLES, ncclFloat64,
                                             (ncclComm_t)c->comm, c->stream));
         ICPB_TRY(solve_launch(c, rank_b, c->n_ranks));
+        ICPB_CUDA(c, cudaEventRecord(c->ev[8], c->stream));
         ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
-        {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
-            out->ms_nn_total += ms;
-            if (iter == 0) out->ms_nn_first = ms;
-        }
+        float nn_ms = 0.f, iter_ms = 0.f;
+        cudaEventElapsedTime(&nn_ms, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&iter_ms, c->ev[0], c->ev[8]);
+        out->ms_nn_total += nn_ms;
+        if (iter == 0) out->ms_nn_first = nn_ms;
         const IterRecord rec = *c->h_rec;
         if (rec.problems > 0.0) log_msg(c, "warning: %.0f abnormal distance values", rec.problems);
         log_msg(c, "  distance range: min=%.6f, max=%.6f", rec.dmin, rec.dmax);
@@ -250,6 +250,8 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         it.rmse = rec.rmse;
         it.valid_points = rec.valid_points;
         it.outlier_points = rec.outlier_points;
+        it.nn_ms = nn_ms;
+        it.iter_ms = iter_ms;
         std::memcpy(it.transform, rec.T_cum, sizeof it.transform);
 
         if (rec.exit_code == 1) {  // converged: icpengine.cpp:291-305 ; CLI :551-554
@@ -425,6 +427,8 @@ int icp_create(icp_handle* out, int device_id) {
     for (auto& e : c->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaMalloc(&c->d_state, sizeof(LoopState)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    if (cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    cudaMemset(c->d_counters, 0, 2 * sizeof(unsigned long long));
     if (cudaHostAlloc(&c->h_rec, sizeof(IterRecord), cudaHostAllocMapped) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaHostGetDevicePointer(&c->d_rec, c->h_rec, 0) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     const char* m = getenv("ICP_B200_NN_MODE");
@@ -444,6 +448,7 @@ void icp_destroy(icp_handle h) {
                       &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b};
     for (DevBuf* b : bufs) devbuf_free(*b);
     if (c->d_state) cudaFree(c->d_state);
+    if (c->d_counters) cudaFree(c->d_counters);
     if (c->h_rec) cudaFreeHost(c->h_rec);
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
@@ -499,6 +504,19 @@ int icp_set_option(icp_handle h, const char* key, double value) {
         c->err = std::string("unknown option ") + key;
         return ICP_INVALID_ARGUMENT;
     }
+    return ICP_OK;
+}
+
+int icp_nn_counters(icp_handle h, int64_t* fast_path, int64_t* literal_fallback, int reset) {
+    Ctx* c = (Ctx*)h;
+    if (!c) return ICP_INVALID_ARGUMENT;
+    ICPB_CUDA(c, cudaSetDevice(c->device));
+    unsigned long long v[2] = {0, 0};
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    ICPB_CUDA(c, cudaMemcpy(v, c->d_counters, sizeof v, cudaMemcpyDeviceToHost));
+    if (fast_path) *fast_path = (int64_t)v[0];
+    if (literal_fallback) *literal_fallback = (int64_t)v[1];
+    if (reset) ICPB_CUDA(c, cudaMemset(c->d_counters, 0, sizeof v));
     return ICP_OK;
 }
 

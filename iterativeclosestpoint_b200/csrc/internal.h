@@ -34,7 +34,7 @@ struct NcclApi;  // comm.cu
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[12] = {};
     std::string err;
     icp_params params;
     icp_iteration_cb on_iteration = nullptr;
@@ -61,6 +61,7 @@ struct Ctx {
     bool opt_order_queries = true;   // Morton-order the source for traversal coherence
     bool opt_write_mask = false;     // keep the per-point inlier mask of the last iteration
     LoopState* d_state = nullptr;
+    unsigned long long* d_counters = nullptr;  // [0] fast-path answers, [1] literal fallbacks
     IterRecord* h_rec = nullptr;  // pinned, device-mapped
     IterRecord* d_rec = nullptr;
 

@@ -4,19 +4,22 @@
 //
 // The answer of the reference is defined by its traversal: depth-first, children ordered by the ROOTED box
 // distance (ties keep octant order), a node skipped when fl(fl(sqrt(s))^2) >= best, points accepted on a
-// strict <.  This kernel executes exactly that traversal with an explicit per-thread stack in shared memory
-// (`dfs`), so indices agree bit-for-bit including every tie.
+// strict <.  `dfs_literal` executes exactly that traversal with an explicit per-thread stack in shared
+// memory, so its indices agree with the reference bit for bit including every tie.
 //
-// Two provably result-preserving accelerations are layered on top (DESIGN.md "NN query"):
-//   * seeding    -- the traversal is started with best = hi, a hair above the squared distance S of a real
-//                   target point (found by point location, or last iteration's match).  While nothing has
-//                   been accepted yet, any quantity compared against `best` that falls into the guard band
-//                   [hi, hi2] marks the query ambiguous and it is redone unseeded; otherwise the seeded and
-//                   the unseeded traversals make the same accept/prune decisions from the first accepted
-//                   point on, hence return the same index.
-//   * subtree    -- if the query lies inside node A's box with clearance c, c^2 > hi3 > hi2, every node
-//     start         outside A's subtree has box distance above the band and would be pruned whenever it is
-//                   reached, so the traversal may start at A instead of the root.
+// Fast path (mode 1) -- result-preserving by the following argument (DESIGN.md "NN query"):
+//   Let s(p) be the reference's squared-distance expression and suppose one target point P has
+//   s(P) * (1 + 2^-40) < s(p) for every other point p.  Then the reference returns P whatever its visiting
+//   order: an ancestor box N of P has fl(fl(sqrt(sbox))^2) <= s(P)(1+u)^3, which is below any `best` the
+//   reference can hold before it has scanned P (the initial value or some other point's s), so P's leaf is
+//   never pruned, P is accepted on the strict <, and nothing can replace it afterwards.
+//   The fast path therefore only has to find the exact minimum of s and PROVE the margin.  It searches the
+//   same octree with an un-rooted box bound (sbox <= s(p) for every p in the box, by monotonicity of the
+//   rounded operations), keeps the two smallest s it sees, prunes only boxes with sbox > min(best, seed) *
+//   (1 + 2^-39), and starts at the deepest node around the query whose clearance squared exceeds the seed bound
+//   (every box outside that node is farther than the bound).  Any point it did not look at has
+//   s > best (1 + 2^-39).  If second <= best (1 + 2^-40) (exact ties, duplicates, 1-ulp near ties) the query
+//   is re-run through `dfs_literal`; otherwise the unique minimum is the reference's answer.
 #include "internal.h"
 
 namespace icpb {
@@ -25,6 +28,7 @@ constexpr int NN_THREADS = 128;
 constexpr int NN_MAX_LEVELS = 22;           // octree_max_depth <= 21  => at most 22 levels on a path
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr int SEED_SCAN = 8;                // points inspected to seed a query
+#define ICPB_INF __longlong_as_double(0x7FF0000000000000LL)
 
 struct NNArgs {
     const Node* __restrict__ nodes;
@@ -41,8 +45,9 @@ struct NNArgs {
     const uint32_t* prev_pos;  // last iteration's match per query (may be null)
     StatA* part_a;
     const LoopState* state;
+    unsigned long long* counters;  // [0] queries answered by the fast path, [1] literal fallbacks (may be null)
     int apply_pending;
-    int mode;                  // 0: literal traversal from the root; 1: seeded + subtree start
+    int mode;                  // 0: literal traversal from the root; 1: fast path + literal fallback
     double init_best;
     uint32_t pos_of_idx0;
 };
@@ -88,17 +93,16 @@ struct Search {
     double best;       // best squared distance so far
     uint32_t pos;      // its position in the sorted target, NONE while nothing accepted
     uint32_t idx;      // its original index
-    bool ambiguous;    // a compared quantity fell into the guard band before the first acceptance
 };
 
-// The reference traversal from node `start` (whose own prune test the caller has already made).
-// track: guard-band bookkeeping for seeded runs.  stk: this thread's column of the shared stack.
-template <bool TRACK>
-__device__ __forceinline__ void dfs(const Node* __restrict__ nodes, const TPoint* __restrict__ pts, const double qx,
-                                    const double qy, const double qz, uint32_t start, Search& S, const double band_lo,
-                                    const double band_hi, uint2* stk /* stride NN_THREADS */) {
+// ---------------------------------------------------------------------------------------------------
+// The reference traversal from the root (whose own prune test the caller has already made).
+// stk: this thread's column of the shared stack (row stride NN_THREADS).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dfs_literal(const Node* __restrict__ nodes, const TPoint* __restrict__ pts, const double qx,
+                                            const double qy, const double qz, Search& S, uint2* stk) {
     int sp = 0;
-    uint32_t cur = start;
+    uint32_t cur = 0;
     bool have_cur = true;
     for (;;) {
         if (have_cur) {
@@ -114,7 +118,6 @@ __device__ __forceinline__ void dfs(const Node* __restrict__ nodes, const TPoint
                     uint32_t pidx;
                     load_point(pts, nd.pt0 + k, px, py, pz, pidx);
                     const double d2 = sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz));
-                    if (TRACK && S.pos == NONE && d2 >= band_lo && d2 <= band_hi) S.ambiguous = true;
                     if (d2 < S.best || (from_this_leaf && d2 == S.best && pidx < S.idx)) {
                         S.best = d2;
                         S.pos = nd.pt0 + k;
@@ -139,7 +142,7 @@ __device__ __forceinline__ void dfs(const Node* __restrict__ nodes, const TPoint
 #pragma unroll
                 for (int o = 0; o < 8; ++o) {
                     const double s = dadd(dadd((o & 1) ? dh[0] : dl[0], (o & 2) ? dh[1] : dl[1]), (o & 4) ? dh[2] : dl[2]);
-                    md[o] = ((mask >> o) & 1u) ? dsqrt(s) : __longlong_as_double(0x7FF0000000000000LL);
+                    md[o] = ((mask >> o) & 1u) ? dsqrt(s) : ICPB_INF;
                 }
                 // rank = position after a stable ascending sort by md (std::sort on <= 8 items == insertion sort)
                 uint32_t word = 0;
@@ -157,7 +160,6 @@ __device__ __forceinline__ void dfs(const Node* __restrict__ nodes, const TPoint
                 }
                 const uint32_t cnt = __popc(mask);
                 const double m0 = dmul(mdmin, mdmin);
-                if (TRACK && S.pos == NONE && m0 >= band_lo && m0 <= band_hi) S.ambiguous = true;
                 if (m0 >= S.best) {
                     have_cur = false;  // nearest child pruned => all children pruned (octree.cpp:134-135)
                 } else {
@@ -186,7 +188,6 @@ __device__ __forceinline__ void dfs(const Node* __restrict__ nodes, const TPoint
             }
             const double mdc = dsqrt(sumsq3(d[0], d[1], d[2]));
             const double m = dmul(mdc, mdc);
-            if (TRACK && S.pos == NONE && m >= band_lo && m <= band_hi) S.ambiguous = true;
             if (m >= S.best) {
                 --sp;  // this sibling and every later one (larger distance) are pruned
                 continue;
@@ -201,6 +202,95 @@ __device__ __forceinline__ void dfs(const Node* __restrict__ nodes, const TPoint
             cur = pn.child0 + __popc(mask & ((1u << oct) - 1u));
             have_cur = true;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fast path: exact minimum of s and the runner-up, un-rooted bounds, any visiting order.
+// Stack entries: x = child0 of the parent, y = parent's child mask | (octants still to visit << 8).
+// ---------------------------------------------------------------------------------------------------
+struct Fast {
+    double best, second, bound;
+    uint32_t pos;
+};
+
+__device__ __forceinline__ void fast_take(Fast& F, double s, uint32_t pos) {
+    const double grow = 1.0 + 1.8189894035458565e-12;  // 1 + 2^-39
+    if (s < F.best) {
+        F.second = F.best;
+        F.best = s;
+        F.pos = pos;
+        const double b = dmul(s, grow);
+        F.bound = b < F.bound ? b : F.bound;
+    } else if (s < F.second) {
+        F.second = s;
+    }
+}
+
+__device__ __forceinline__ void fast_search(const Node* __restrict__ nodes, const TPoint* __restrict__ pts, const double qx,
+                                            const double qy, const double qz, uint32_t start, Fast& F, uint2* stk) {
+    uint2* top = stk;  // one past the last entry of this thread's column
+    uint32_t cur = start;
+    for (;;) {
+        const NodeRegs nd = load_node(nodes, cur);
+        const uint32_t mask = nd.meta & 0xFFu;
+        bool descend = false;
+        if (mask == 0) {
+            const double sb = sumsq3(axis_dist(nd.lo[0], nd.hi[0], qx), axis_dist(nd.lo[1], nd.hi[1], qy),
+                                     axis_dist(nd.lo[2], nd.hi[2], qz));
+            if (sb <= F.bound) {
+                for (uint32_t k = 0; k < nd.npts; ++k) {
+                    double px, py, pz;
+                    uint32_t pidx;
+                    load_point(pts, nd.pt0 + k, px, py, pz, pidx);
+                    fast_take(F, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)), nd.pt0 + k);
+                }
+            }
+        } else {
+            double dl[3], dh[3];
+            const double q[3] = {qx, qy, qz};
+            uint32_t oq = 0;  // octant of the query inside this node (visited first: it tightens the bound)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double mid = dmul(dadd(nd.lo[a], nd.hi[a]), 0.5);
+                const double l = axis_dist(nd.lo[a], mid, q[a]);
+                const double h = axis_dist(mid, nd.hi[a], q[a]);
+                dl[a] = dmul(l, l);
+                dh[a] = dmul(h, h);
+                oq |= (q[a] > mid ? 1u : 0u) << a;
+            }
+            uint32_t surv = 0;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const double s = dadd(dadd((o & 1) ? dh[0] : dl[0], (o & 2) ? dh[1] : dl[1]), (o & 4) ? dh[2] : dl[2]);
+                surv |= (s <= F.bound ? 1u : 0u) << o;
+            }
+            surv &= mask;
+            if (surv) {
+                const uint32_t o = ((surv >> oq) & 1u) ? oq : (uint32_t)(__ffs(surv) - 1);
+                surv &= ~(1u << o);
+                if (surv) {
+                    *top = make_uint2(nd.child0, mask | (surv << 8));
+                    top += NN_THREADS;
+                }
+                cur = nd.child0 + __popc(mask & ((1u << o) - 1u));
+                descend = true;
+            }
+        }
+        if (descend) continue;
+        // next pending sibling
+        if (top == stk) break;
+        uint2 e = *(top - NN_THREADS);
+        uint32_t surv = e.y >> 8;
+        const uint32_t o = (uint32_t)(__ffs(surv) - 1);
+        surv &= surv - 1u;
+        if (surv) {
+            e.y = (e.y & 0xFFu) | (surv << 8);
+            *(top - NN_THREADS) = e;
+        } else {
+            top -= NN_THREADS;
+        }
+        cur = e.x + __popc((e.y & 0xFFu) & ((1u << o) - 1u));
     }
 }
 
@@ -230,6 +320,7 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
 
     StatA st;
     st.n = 0.0; st.mean = 0.0; st.m2 = 0.0; st.dmin = DBL_MAX; st.dmax = 0.0; st.problems = 0.0;
+    bool fell_back = false;
 
     if (active) {
         double qx = A.sx[i], qy = A.sy[i], qz = A.sz[i];
@@ -244,13 +335,9 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
             A.oy[i] = qy;
             A.oz[i] = qz;
         }
-        Search S;
-        S.best = A.init_best;
-        S.pos = NONE;
-        S.idx = 0;
-        S.ambiguous = false;
         const bool finite_q = isfinite(qx) && isfinite(qy) && isfinite(qz);
-        bool need_full = finite_q;
+        uint32_t result = NONE;
+        bool need_literal = finite_q;
         if (A.mode == 1 && finite_q) {
             // ---- point location: walk down the cell path of q, remembering each level's clearance ----
             uint32_t n = 0;
@@ -277,7 +364,7 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
                 path += NN_THREADS;
             }
             // ---- seed: squared distance of a real target point ----
-            double Sd = __longlong_as_double(0x7FF0000000000000LL);
+            double Sd = ICPB_INF;
             const uint32_t ns = nd.npts < (uint32_t)SEED_SCAN ? nd.npts : (uint32_t)SEED_SCAN;
             for (uint32_t k = 0; k < ns; ++k) {
                 double px, py, pz;
@@ -294,39 +381,47 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
                     Sd = fmin(Sd, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)));
                 }
             }
-            const double eps = 9.094947017729282e-13;  // 2^-40
-            const double hi = dadd(dmul(Sd, 1.0 + eps), 1e-300);
-            const double hi2 = dmul(hi, 1.0 + eps);
-            const double hi3 = dmul(hi2, 1.0 + eps);
-            if (hi3 < A.init_best) {  // also false for inf/NaN
-                // ---- subtree start: deepest path node whose clearance^2 clears the band ----
+            if (Sd < 1e19) {  // also false for inf/NaN; keeps clear of the CLI's initial best 1e20
+                Fast F;
+                F.best = ICPB_INF;
+                F.second = ICPB_INF;
+                F.pos = NONE;
+                F.bound = dmul(Sd, 1.0 + 1.8189894035458565e-12);                // S (1 + 2^-39)
+                const double clear_req = dmul(Sd, 1.0 + 3.637978807091713e-12);  // S (1 + 2^-38)
+                // ---- subtree start: deepest path node whose clearance^2 exceeds the seed bound ----
                 uint32_t start = 0;
                 for (int l = level; l > 0; --l) {
-                    const uint2 e = stk[l * NN_THREADS];
+                    const uint2 e = *path;
+                    path -= NN_THREADS;
                     const double cf = (double)__uint_as_float(e.y);
-                    if (cf * cf > hi3) {
+                    if (cf * cf > clear_req) {
                         start = e.x;
                         break;
                     }
                 }
-                S.best = hi;
-                dfs<true>(A.nodes, A.pts, qx, qy, qz, start, S, hi, hi2, stk);
-                need_full = S.ambiguous || S.pos == NONE;
+                fast_search(A.nodes, A.pts, qx, qy, qz, start, F, stk);
+                // unique minimum with margin 2^-40 => order-independent => the reference's answer
+                if (F.pos != NONE && F.second > dmul(F.best, 1.0 + 9.094947017729282e-13)) {
+                    result = F.pos;
+                    need_literal = false;
+                }
             }
         }
-        if (need_full) {
+        if (need_literal) {
             // ---- the reference traversal from the root (octree.cpp:175-184) ----
+            Search S;
             S.best = A.init_best;
             S.pos = NONE;
             S.idx = 0;
-            S.ambiguous = false;
             const NodeRegs root = load_node(A.nodes, 0);
             const double mdr = dsqrt(sumsq3(axis_dist(root.lo[0], root.hi[0], qx), axis_dist(root.lo[1], root.hi[1], qy),
                                             axis_dist(root.lo[2], root.hi[2], qz)));
-            if (!(dmul(mdr, mdr) >= S.best)) dfs<false>(A.nodes, A.pts, qx, qy, qz, 0u, S, 0.0, 0.0, stk);
+            if (!(dmul(mdr, mdr) >= S.best)) dfs_literal(A.nodes, A.pts, qx, qy, qz, S, stk);
+            result = S.pos;
+            fell_back = true;
         }
         // findNearest returns index 0 when nothing was accepted (best_idx = 0 initially, octree.cpp:179)
-        const uint32_t pos = (S.pos == NONE) ? A.pos_of_idx0 : S.pos;
+        const uint32_t pos = (result == NONE) ? A.pos_of_idx0 : result;
         double px, py, pz;
         uint32_t pidx;
         load_point(A.pts, pos, px, py, pz, pidx);
@@ -341,6 +436,14 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
             st.dmax = d;
         } else {
             st.problems = 1.0;
+        }
+    }
+    if (A.counters && A.mode == 1) {
+        const unsigned fb = __ballot_sync(0xffffffffu, fell_back);
+        const unsigned ac = __ballot_sync(0xffffffffu, active);
+        if ((threadIdx.x & 31) == 0) {
+            if (fb) atomicAdd(&A.counters[1], (unsigned long long)__popc(fb));
+            atomicAdd(&A.counters[0], (unsigned long long)__popc(ac & ~fb));
         }
     }
     if (A.part_a) {
@@ -371,6 +474,7 @@ int nn_launch(Ctx* c, const NNLaunch& L) {
     A.prev_pos = L.prev_pos;
     A.part_a = L.part_a;
     A.state = L.state;
+    A.counters = c->d_counters;
     A.apply_pending = L.apply_pending;
     A.mode = L.mode;
     A.init_best = L.init_best;

@@ -57,6 +57,8 @@ class IterationResult:  # core/icpengine.h:24-32
     rotationAngle: float = float("nan")
     translationDistance: float = float("nan")
     hasAngles: bool = True
+    nnMs: float = 0.0
+    iterMs: float = 0.0
 
 
 @dataclass
@@ -144,6 +146,12 @@ class Handle:
 
     def kernel_launches(self) -> int:
         return int(self.lib.icp_kernel_launches(self.h))
+
+    def nn_counters(self, reset=True):
+        """(queries answered by the fast path, queries re-run through the literal traversal) since the last reset."""
+        a = C.c_int64(); b = C.c_int64()
+        self.check(self.lib.icp_nn_counters(self.h, C.byref(a), C.byref(b), 1 if reset else 0))
+        return a.value, b.value
 
     # -- whole path ---------------------------------------------------------------------------------
     def _result(self, cap):
@@ -271,6 +279,8 @@ def _iteration_from_c(it) -> IterationResult:
     r.outlierPoints = int(it.outlier_points)
     r.transform = np.array(list(it.transform), dtype=np.float64).reshape(4, 4)
     r.hasAngles = bool(it.has_angles)
+    r.nnMs = float(it.nn_ms)
+    r.iterMs = float(it.iter_ms)
     if r.hasAngles:
         r.rotationAngle = float(it.rotation_angle)
         r.translationDistance = float(it.translation_distance)
