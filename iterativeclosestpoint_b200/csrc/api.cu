@@ -15,14 +15,14 @@
 namespace icpb {
 
 // iter.cu / build.cu entry points not in internal.h
-int stage_a_finish(Ctx* c, const StatA* part, int n_part, StatA* rank_part_slot, const StatA* all_rank_parts, int n_ranks,
-                   int iter, bool finalize);
-int stage_a_finalize(Ctx* c, const StatA* all_rank_parts, int n_ranks, int iter);
+int stat_a_blocks(Ctx* c, int64_t n);
+int stat_a_launch(Ctx* c, const double* dist, int64_t n, StatA* part, StatA* rank_slot);
+int stage_a_reduce_launch(Ctx* c, const StatA* part, int n_part, StatA* rank_part_slot);
 int dist_from_idx_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const int32_t* idx, int64_t n,
                          uint32_t* pos_out, double* dist_out, StatA* part, int* n_part);
 int stage_b_blocks(Ctx* c, int64_t n);
 int stage_b_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const uint32_t* pos, const double* dist,
-                   int64_t n, uint8_t* mask_out, double* part, double* rank_part_slot);
+                   int64_t n, int iter, const StatA* rank_a, uint8_t* mask_out, double* part, double* rank_b);
 int pairs_b_launch(Ctx* c, const double* a_xyz, const double* b_xyz, int64_t n, double* part, double* out17);
 int solve_launch(Ctx* c, const double* rank_parts, int n_ranks);
 int bestfit_launch(Ctx* c, const double* b17, const double* a0, const double* b0, double* T_out);
@@ -97,7 +97,8 @@ static int ensure_run_buffers(Ctx* c, int64_t n) {
     ICPB_TRY(devbuf_reserve(c, c->pos, (size_t)n * sizeof(uint32_t)));
     ICPB_TRY(devbuf_reserve(c, c->dist, (size_t)n * sizeof(double)));
     ICPB_TRY(devbuf_reserve(c, c->mask, (size_t)n));
-    const size_t nbA = (size_t)nn_grid_blocks(n) + 1024;
+    ICPB_TRY(devbuf_reserve(c, c->node_io, (size_t)n * sizeof(uint32_t)));
+    const size_t nbA = (size_t)std::max<int64_t>(stat_a_blocks(c, n), (n + 255) / 256 / 4) + 1024;
     ICPB_TRY(devbuf_reserve(c, c->part_a, nbA * sizeof(StatA)));
     ICPB_TRY(devbuf_reserve(c, c->part_b, (size_t)(stage_b_blocks(c, n) + 8) * STATB_DOUBLES * sizeof(double)));
     ICPB_TRY(devbuf_reserve(c, c->gather_a, (size_t)std::max(c->n_ranks, 1) * sizeof(StatA) + 64));
@@ -119,13 +120,14 @@ static void identity16(double* T) {
 
 // rotationAngle / translationDistance of a cumulative transform (icpengine.cpp:356-362); evaluated on the host
 // with the C library's acos, as the reference does.  Summation orders follow the reference build's Eigen
-// reductions (trace = a0 + (a1 + a2), squared norm likewise).
+// reductions, pinned by tests/golden/engine_*.npz: trace = a0 + (a1 + a2) (unrolled scalar redux), squared norm of
+// the translation block = (t0^2 + t1^2) + t2^2 (packet first, scalar tail).
 static void angles_of(const double* T, double* angle_deg, double* trans) {
     volatile double tr = T[0] + (T[5] + T[10]);
     *angle_deg = std::acos((tr - 1.0) / 2.0) * 180.0 / M_PI;
     volatile double a = T[3] * T[3], b = T[7] * T[7], cc = T[11] * T[11];
-    volatile double s = b + cc;
-    *trans = std::sqrt(a + s);
+    volatile double s = a + b;
+    *trans = std::sqrt(s + cc);
 }
 
 // Upload a host AoS cloud into `stage` (device) -- pinned staging is left to the caller's allocator; plain
@@ -203,7 +205,8 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         L.pos_out = (uint32_t*)c->pos.p;
         L.dist_out = (double*)c->dist.p;
         L.prev_pos = (iter > 0 && c->opt_nn_mode == 1) ? (uint32_t*)c->pos.p : nullptr;
-        L.part_a = part_a;
+        L.node_io = (c->opt_nn_mode == 1) ? (uint32_t*)c->node_io.p : nullptr;
+        L.part_a = nullptr;
         L.state = c->d_state;
         L.apply_pending = 1;
         L.mode = c->opt_nn_mode;
@@ -212,21 +215,19 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         ICPB_TRY(nn_launch(c, L));
         ICPB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
 
-        const int nbA = nn_grid_blocks(n);
-        if (c->n_ranks > 1) {
-            ICPB_TRY(stage_a_finish(c, part_a, nbA, rank_a + c->rank, rank_a, c->n_ranks, iter, false));
+        // stage A: this rank's Chan partial of the distances; ranks exchange partials, every rank merges them in rank order
+        ICPB_TRY(stat_a_launch(c, L.dist_out, n, part_a, rank_a + c->rank));
+        if (c->n_ranks > 1)
             ICPB_NCCL(c, c->nccl->AllGather(rank_a + c->rank, rank_a, sizeof(StatA) / sizeof(double), ncclFloat64,
                                             (ncclComm_t)c->comm, c->stream));
-            ICPB_TRY(stage_a_finalize(c, rank_a, c->n_ranks, iter));
-        } else {
-            ICPB_TRY(stage_a_finish(c, part_a, nbA, rank_a, rank_a, 1, iter, true));
-        }
-        ICPB_TRY(stage_b_launch(c, L.sx, L.sy, L.sz, L.pos_out, L.dist_out, n, c->opt_write_mask ? (uint8_t*)c->mask.p : nullptr,
-                                part_b, rank_b + (size_t)c->rank * STATB_DOUBLES));
-        if (c->n_ranks > 1)
+        // stage B (+ the solve on a single rank)
+        ICPB_TRY(stage_b_launch(c, L.sx, L.sy, L.sz, L.pos_out, L.dist_out, n, iter, rank_a,
+                                c->opt_write_mask ? (uint8_t*)c->mask.p : nullptr, part_b, rank_b));
+        if (c->n_ranks > 1) {
             ICPB_NCCL(c, c->nccl->AllGather(rank_b + (size_t)c->rank * STATB_DOUBLES, rank_b, STATB_DOUBLES, ncclFloat64,
                                             (ncclComm_t)c->comm, c->stream));
-        ICPB_TRY(solve_launch(c, rank_b, c->n_ranks));
+            ICPB_TRY(solve_launch(c, rank_b, c->n_ranks));
+        }
         ICPB_CUDA(c, cudaEventRecord(c->ev[8], c->stream));
         ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
         float nn_ms = 0.f, iter_ms = 0.f;
@@ -445,7 +446,7 @@ void icp_destroy(icp_handle h) {
     icp_comm_destroy(h);
     octree_free(c);
     DevBuf* bufs[] = {&c->tgt_raw, &c->sx, &c->sy, &c->sz, &c->sperm, &c->pos, &c->dist, &c->mask, &c->part_a, &c->part_b,
-                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b};
+                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io};
     for (DevBuf* b : bufs) devbuf_free(*b);
     if (c->d_state) cudaFree(c->d_state);
     if (c->d_counters) cudaFree(c->d_counters);
@@ -645,6 +646,7 @@ int icp_nn_query(icp_handle h, const double* q_xyz, int64_t n, int32_t* idx_out,
     L.pos_out = (uint32_t*)c->pos.p;
     L.dist_out = (double*)c->dist.p;
     L.prev_pos = nullptr;
+    L.node_io = nullptr;
     L.part_a = nullptr;
     L.state = nullptr;
     L.apply_pending = 0;
@@ -699,9 +701,15 @@ int icp_iteration_stats(icp_handle h, const double* src_xyz, int64_t n, const in
     int n_part = 0;
     ICPB_TRY(dist_from_idx_launch(c, sx, sy, sz, (const int32_t*)c->scratch1.p, n, (uint32_t*)c->pos.p, (double*)c->dist.p, part_a,
                                   &n_part));
-    ICPB_TRY(stage_a_finish(c, part_a, n_part, rank_a, rank_a, 1, iteration, true));
-    ICPB_TRY(stage_b_launch(c, sx, sy, sz, (uint32_t*)c->pos.p, (double*)c->dist.p, n, (uint8_t*)c->mask.p, (double*)c->part_b.p, rank_b));
-    ICPB_TRY(solve_launch(c, rank_b, 1));
+    ICPB_TRY(stage_a_reduce_launch(c, part_a, n_part, rank_a));
+    const int keep_ranks = c->n_ranks, keep_rank = c->rank;
+    c->n_ranks = 1;  // the stage API is per handle: no exchange
+    c->rank = 0;
+    int sb = stage_b_launch(c, sx, sy, sz, (uint32_t*)c->pos.p, (double*)c->dist.p, n, iteration, rank_a, (uint8_t*)c->mask.p,
+                            (double*)c->part_b.p, rank_b);
+    c->n_ranks = keep_ranks;
+    c->rank = keep_rank;
+    ICPB_TRY(sb);
     ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
     const IterRecord rec = *c->h_rec;
     if (dist_out) ICPB_CUDA(c, cudaMemcpy(dist_out, c->dist.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));

@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(128) node_count_kernel(const Node* __restrict_
 __global__ void __launch_bounds__(128) node_emit_kernel(Node* __restrict__ nodes, uint32_t first, uint32_t count,
                                                         const uint64_t* __restrict__ keys, int level, int max_pts,
                                                         int max_depth, const uint32_t* __restrict__ child_off,
-                                                        uint32_t next_first, uint32_t* __restrict__ leaf_counter) {
+                                                        uint32_t next_first, uint32_t* __restrict__ leaf_counter,
+                                                        uint32_t* __restrict__ parent) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     Node nd = nodes[first + t];
@@ -423,6 +424,7 @@ __global__ void __launch_bounds__(128) node_emit_kernel(Node* __restrict__ nodes
             ch.npts = e - b;
             ch.meta = ((uint32_t)(level + 1) << 8);
             nodes[c0 + k] = ch;
+            parent[c0 + k] = first + t;
             mask |= 1u << oct;
             ++k;
         }
@@ -454,6 +456,7 @@ __global__ void inv_perm_kernel(const TPoint* __restrict__ pts, int64_t n, uint3
 void octree_free(Ctx* c) {
     DeviceOctree& t = c->tree;
     if (t.nodes) cudaFree(t.nodes);
+    if (t.parent) cudaFree(t.parent);
     if (t.pts) cudaFree(t.pts);
     if (t.inv_perm) cudaFree(t.inv_perm);
     t = DeviceOctree();
@@ -464,13 +467,18 @@ static int grow_nodes(Ctx* c, int64_t need) {
     if (need <= t.cap_nodes) return ICP_OK;
     int64_t cap = std::max<int64_t>(need + need / 2, 1024);
     Node* nn = nullptr;
+    uint32_t* np = nullptr;
     ICPB_CUDA(c, cudaMalloc(&nn, (size_t)cap * sizeof(Node)));
+    ICPB_CUDA(c, cudaMalloc(&np, (size_t)cap * sizeof(uint32_t)));
     if (t.nodes) {
         ICPB_CUDA(c, cudaMemcpyAsync(nn, t.nodes, (size_t)t.n_nodes * sizeof(Node), cudaMemcpyDeviceToDevice, c->stream));
+        ICPB_CUDA(c, cudaMemcpyAsync(np, t.parent, (size_t)t.n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
         ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
         ICPB_CUDA(c, cudaFree(t.nodes));
+        ICPB_CUDA(c, cudaFree(t.parent));
     }
     t.nodes = nn;
+    t.parent = np;
     t.cap_nodes = cap;
     return ICP_OK;
 }
@@ -524,6 +532,7 @@ int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int
 
     // K3
     ICPB_TRY(grow_nodes(c, std::max<int64_t>(m / 2, 1024)));
+    ICPB_CUDA(c, cudaMemsetAsync(t.parent, 0xFF, sizeof(uint32_t), s));
     root_node_kernel<<<1, 32, 0, s>>>(t.nodes, d_root, (uint32_t)m);
     c->launches++;
     t.n_nodes = 1;
@@ -542,7 +551,7 @@ int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int
         const uint32_t next_first = first + count;
         ICPB_TRY(grow_nodes(c, (int64_t)next_first + n_children));
         node_emit_kernel<<<nb, 128, 0, s>>>(t.nodes, first, count, keys, level, max_pts, max_depth, offs, next_first,
-                                            d_misc + 1);
+                                            d_misc + 1, t.parent);
         c->launches++;
         t.n_nodes = (int64_t)next_first + n_children;
         if (n_children == 0) break;

@@ -11,6 +11,7 @@ namespace icpb {
 
 struct DeviceOctree {
     Node* nodes = nullptr;
+    uint32_t* parent = nullptr;  // parent node index per node (root: 0xFFFFFFFF)
     int64_t n_nodes = 0, cap_nodes = 0;
     TPoint* pts = nullptr;  // Morton-sorted target points (xyz + original index)
     int64_t n_pts = 0;
@@ -52,6 +53,7 @@ struct Ctx {
     DevBuf sx, sy, sz, sperm;  // SoA coordinates + original index of each internal slot
     int64_t n_src = 0;
     DevBuf pos, dist, mask;    // per-query NN result (sorted target position), distance, inlier mask
+    DevBuf node_io;            // per-query leaf of the last match (temporal start of the next search)
     DevBuf part_a, part_b;     // per-block partials
     DevBuf scratch0, scratch1, scratch2, scratch3, scratch_src;
     bool src_identity_perm = false;  // resident source is in caller order (no permutation)
@@ -112,6 +114,7 @@ struct NNLaunch {
     uint32_t* pos_out;     // sorted target position of the NN
     double* dist_out;      // distance
     const uint32_t* prev_pos;  // last iteration's match per query, seeds the search (may be null)
+    uint32_t* node_io;         // in: node the previous search started from; out: this one's (may be null)
     StatA* part_a;         // per-block partial (may be null: no statistics)
     const LoopState* state;  // may be null (stateless query)
     int apply_pending;     // read state->have_T / T_pending and transform on load

@@ -28,60 +28,111 @@ __device__ __forceinline__ StatA stat_empty() {
     return s;
 }
 
-// one block: merges `n_part` partials into out[0] (fixed order: strided per thread, then a binary tree)
-__global__ void __launch_bounds__(RED_THREADS) stage_a_reduce_kernel(const StatA* __restrict__ part, int n_part,
-                                                                     StatA* __restrict__ out) {
-    __shared__ StatA sm[RED_THREADS];
-    // contiguous chunk per thread keeps the merge order = index order
-    const int per = (n_part + RED_THREADS - 1) / RED_THREADS;
-    const int b = threadIdx.x * per, e = min(n_part, b + per);
-    StatA acc = stat_empty();
-    for (int k = b; k < e; ++k) acc = stat_merge(acc, part[k]);
+// Distances -> per-block Chan partials -> (last block) this rank's partial.  Each thread owns a fixed set of
+// elements and the merges follow a fixed tree, so the result does not depend on scheduling.
+__device__ __forceinline__ void stat_push(StatA& a, double d) {
+    // Welford update == stat_merge(a, {1, d, 0})
+    a.n += 1.0;
+    const double delta = d - a.mean;
+    a.mean += delta / a.n;
+    a.m2 += delta * (d - a.mean);
+    if (isfinite(d)) {
+        a.dmin = fmin(a.dmin, d);
+        a.dmax = fmax(a.dmax, d);
+    } else {
+        a.problems += 1.0;
+    }
+}
+
+__device__ __forceinline__ StatA stat_block_merge(StatA acc, StatA* sm /* RED_THREADS */) {
     sm[threadIdx.x] = acc;
     __syncthreads();
     for (int s = 1; s < RED_THREADS; s <<= 1) {
         if ((threadIdx.x % (2 * s)) == 0) sm[threadIdx.x] = stat_merge(sm[threadIdx.x], sm[threadIdx.x + s]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[0] = sm[0];
+    return sm[0];
 }
 
-// merges the per-rank partials in rank order and derives mean / std / threshold
-__global__ void stage_a_finalize_kernel(LoopState* __restrict__ st, const StatA* __restrict__ rank_part, int n_ranks,
-                                        int iter) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    StatA a = rank_part[0];
-    for (int r = 1; r < n_ranks; ++r) a = stat_merge(a, rank_part[r]);
-    st->a = a;
+__device__ __forceinline__ StatA stat_load_cg(const StatA* p) {
+    StatA r;
+    const double* d = reinterpret_cast<const double*>(p);
+    r.n = __ldcg(d); r.mean = __ldcg(d + 1); r.m2 = __ldcg(d + 2);
+    r.dmin = __ldcg(d + 3); r.dmax = __ldcg(d + 4); r.problems = __ldcg(d + 5);
+    return r;
+}
+
+__global__ void __launch_bounds__(RED_THREADS) stat_a_kernel(const double* __restrict__ dist, int64_t n,
+                                                             StatA* __restrict__ part, unsigned int* __restrict__ ticket,
+                                                             StatA* __restrict__ rank_slot) {
+    __shared__ StatA sm[RED_THREADS];
+    __shared__ bool is_last;
+    // block-contiguous chunk, thread-strided inside it (coalesced, fixed assignment)
+    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t b = (int64_t)blockIdx.x * chunk, e = min(n, b + chunk);
+    StatA acc = stat_empty();
+    for (int64_t i = b + threadIdx.x; i < e; i += RED_THREADS) stat_push(acc, dist[i]);
+    const StatA tot = stat_block_merge(acc, sm);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = tot;
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int n_part = (int)gridDim.x;
+    const int per = (n_part + RED_THREADS - 1) / RED_THREADS;
+    const int pb = threadIdx.x * per, pe = min(n_part, pb + per);
+    StatA a2 = stat_empty();
+    for (int k = pb; k < pe; ++k) a2 = stat_merge(a2, stat_load_cg(part + k));
+    const StatA all = stat_block_merge(a2, sm);
+    if (threadIdx.x == 0) {
+        *rank_slot = all;
+        *ticket = 0u;
+    }
+}
+
+// mean / std / threshold from the rank partials merged in rank order (icpengine.cpp:235-255)
+__device__ __forceinline__ void stat_a_finalize(const LoopState* st, const StatA* rank_part, int n_ranks, int iter, StatA& a,
+                                                double& mean, double& sd, double& thr) {
+    a = stat_load_cg(rank_part);
+    for (int r = 1; r < n_ranks; ++r) a = stat_merge(a, stat_load_cg(rank_part + r));
     const double N = (double)st->n_global;
-    const double mean = a.mean;                 // = (sum d) / N
-    const double sd = dsqrt(ddiv(a.m2, N));     // population std (icpengine.cpp:241-245)
-    double thr;
+    mean = a.mean;                      // = (sum d) / N
+    sd = dsqrt(ddiv(a.m2, N));          // population std (icpengine.cpp:241-245)
     if (st->variant == ICP_VARIANT_ENGINE && iter == 0) {
         thr = dadd(mean, stdmax(dmul(st->sigma, sd), dmul(mean, 0.5)));  // icpengine.cpp:250-252
     } else {
         thr = dadd(mean, dmul(st->sigma, sd));                            // :254 ; CLI :523
     }
-    st->mean = mean;
-    st->std_dev = sd;
-    st->threshold = thr;
-    st->iter = iter;
 }
 
-int stage_a_finish(Ctx* c, const StatA* part, int n_part, StatA* rank_part_slot, const StatA* all_rank_parts,
-                   int n_ranks, int iter, bool finalize) {
-    stage_a_reduce_kernel<<<1, RED_THREADS, 0, c->stream>>>(part, n_part, rank_part_slot);
+int stat_a_blocks(Ctx* c, int64_t n) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>((n + RED_THREADS - 1) / RED_THREADS, (int64_t)c->sm_count * 8));
+}
+
+int stat_a_launch(Ctx* c, const double* dist, int64_t n, StatA* part, StatA* rank_slot) {
+    stat_a_kernel<<<stat_a_blocks(c, n), RED_THREADS, 0, c->stream>>>(dist, n, part, &c->d_state->ticket_a, rank_slot);
     c->launches++;
-    if (finalize) {
-        stage_a_finalize_kernel<<<1, 32, 0, c->stream>>>(c->d_state, all_rank_parts, n_ranks, iter);
-        c->launches++;
-    }
     ICPB_CUDA(c, cudaGetLastError());
     return ICP_OK;
 }
 
-int stage_a_finalize(Ctx* c, const StatA* all_rank_parts, int n_ranks, int iter) {
-    stage_a_finalize_kernel<<<1, 32, 0, c->stream>>>(c->d_state, all_rank_parts, n_ranks, iter);
+// one block: merges `n_part` partials into out[0] (fixed order); used by the stage API
+__global__ void __launch_bounds__(RED_THREADS) stage_a_reduce_kernel(const StatA* __restrict__ part, int n_part,
+                                                                     StatA* __restrict__ out) {
+    __shared__ StatA sm[RED_THREADS];
+    const int per = (n_part + RED_THREADS - 1) / RED_THREADS;
+    const int b = threadIdx.x * per, e = min(n_part, b + per);
+    StatA acc = stat_empty();
+    for (int k = b; k < e; ++k) acc = stat_merge(acc, part[k]);
+    const StatA tot = stat_block_merge(acc, sm);
+    if (threadIdx.x == 0) out[0] = tot;
+}
+
+int stage_a_reduce_launch(Ctx* c, const StatA* part, int n_part, StatA* rank_part_slot) {
+    stage_a_reduce_kernel<<<1, RED_THREADS, 0, c->stream>>>(part, n_part, rank_part_slot);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
     return ICP_OK;
@@ -187,16 +238,37 @@ __device__ __forceinline__ void accb_block_reduce(AccB& acc, double* out /* 17 d
 #pragma unroll
         for (int w = 1; w < RED_THREADS / 32; ++w) v += sm[w][threadIdx.x];
         out[threadIdx.x] = v;
+        __threadfence();
     }
 }
 
-// inlier test + accumulation; each thread owns a contiguous run of queries (fixed geometry => fixed order)
-__global__ void __launch_bounds__(RED_THREADS) stage_b_kernel(const double* __restrict__ sx, const double* __restrict__ sy,
+// forward declarations (defined below)
+__device__ __noinline__ void solve_step(LoopState* st, const double* rank_parts, int n_ranks, IterRecord* rec);
+__device__ __forceinline__ void sum_partials_fixed(const double* part, int n_part, double* out, double* sm);
+
+// Inlier test + accumulation.  Every block derives the threshold from the (already gathered) stage-A rank
+// partials -- identical arithmetic in every block and on every rank -- then owns block-strided tiles (fixed
+// geometry => fixed summation order).  The last block to finish sums the block partials in index order into this
+// rank's slot and, on a single-rank run, goes straight on to the solve.
+__global__ void __launch_bounds__(RED_THREADS, 3) stage_b_kernel(const double* __restrict__ sx, const double* __restrict__ sy,
                                                               const double* __restrict__ sz, const uint32_t* __restrict__ pos,
                                                               const double* __restrict__ dist, int64_t n,
-                                                              const TPoint* __restrict__ pts, const LoopState* __restrict__ st,
-                                                              uint8_t* __restrict__ mask_out, double* __restrict__ part) {
-    const double thr = st->threshold;
+                                                              const TPoint* __restrict__ pts, LoopState* __restrict__ st,
+                                                              const StatA* __restrict__ rank_a, int n_ranks, int rank, int iter,
+                                                              uint8_t* __restrict__ mask_out, double* __restrict__ part,
+                                                              double* __restrict__ rank_b, IterRecord* __restrict__ rec) {
+    __shared__ double s_thr;
+    __shared__ double sm_red[RED_THREADS];
+    __shared__ bool is_last;
+    StatA a_all;
+    double mean = 0.0, sd = 0.0;
+    if (threadIdx.x == 0) {
+        double thr;
+        stat_a_finalize(st, rank_a, n_ranks, iter, a_all, mean, sd, thr);
+        s_thr = thr;
+    }
+    __syncthreads();
+    const double thr = s_thr;
     double pa[3], pb[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -205,7 +277,6 @@ __global__ void __launch_bounds__(RED_THREADS) stage_b_kernel(const double* __re
     }
     AccB acc;
     accb_zero(acc);
-    // block-contiguous tiles, thread-strided inside the tile: coalesced and still a fixed order
     for (int64_t base = (int64_t)blockIdx.x * RED_THREADS; base < n; base += (int64_t)gridDim.x * RED_THREADS) {
         const int64_t i = base + threadIdx.x;
         if (i >= n) break;
@@ -219,6 +290,27 @@ __global__ void __launch_bounds__(RED_THREADS) stage_b_kernel(const double* __re
         }
     }
     accb_block_reduce(acc, part + (int64_t)blockIdx.x * STATB_DOUBLES);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(&st->ticket_b, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    sum_partials_fixed(part, (int)gridDim.x, rank_b + (int64_t)rank * STATB_DOUBLES, sm_red);
+    if (threadIdx.x == 0) {
+        st->ticket_b = 0u;
+        st->a = a_all;
+        st->mean = mean;
+        st->std_dev = sd;
+        st->threshold = thr;
+        st->iter = iter;
+        if (n_ranks == 1) {
+            __threadfence();
+            solve_step(st, rank_b, 1, rec);
+        }
+    }
 }
 
 // explicit pairs (best-fit stage API): all pairs are inliers, pivots = first pair
@@ -241,15 +333,13 @@ __global__ void __launch_bounds__(RED_THREADS) pairs_b_kernel(const double* __re
     accb_block_reduce(acc, part + (int64_t)blockIdx.x * STATB_DOUBLES);
 }
 
-// one block: sums the block partials (fixed order) into out[17]
-__global__ void __launch_bounds__(RED_THREADS) stage_b_reduce_kernel(const double* __restrict__ part, int n_part,
-                                                                     double* __restrict__ out) {
-    __shared__ double sm[RED_THREADS];
+// one block: sums n_part partial records (fixed order: contiguous chunk per thread, then a binary tree)
+__device__ __forceinline__ void sum_partials_fixed(const double* part, int n_part, double* out, double* sm) {
     for (int k = 0; k < STATB_DOUBLES; ++k) {
         const int per = (n_part + RED_THREADS - 1) / RED_THREADS;
         const int b = threadIdx.x * per, e = min(n_part, b + per);
         double v = 0.0;
-        for (int j = b; j < e; ++j) v += part[(int64_t)j * STATB_DOUBLES + k];
+        for (int j = b; j < e; ++j) v += __ldcg(part + (int64_t)j * STATB_DOUBLES + k);
         sm[threadIdx.x] = v;
         __syncthreads();
         for (int s = 1; s < RED_THREADS; s <<= 1) {
@@ -261,16 +351,22 @@ __global__ void __launch_bounds__(RED_THREADS) stage_b_reduce_kernel(const doubl
     }
 }
 
+__global__ void __launch_bounds__(RED_THREADS) stage_b_reduce_kernel(const double* __restrict__ part, int n_part,
+                                                                     double* __restrict__ out) {
+    __shared__ double sm[RED_THREADS];
+    sum_partials_fixed(part, n_part, out, sm);
+}
+
 int stage_b_blocks(Ctx* c, int64_t n) {
     return (int)std::max<int64_t>(1, std::min<int64_t>((n + RED_THREADS - 1) / RED_THREADS, (int64_t)c->sm_count * 8));
 }
 
 int stage_b_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const uint32_t* pos, const double* dist,
-                   int64_t n, uint8_t* mask_out, double* part, double* rank_part_slot) {
+                   int64_t n, int iter, const StatA* rank_a, uint8_t* mask_out, double* part, double* rank_b) {
     const int blocks = stage_b_blocks(c, n);
-    stage_b_kernel<<<blocks, RED_THREADS, 0, c->stream>>>(sx, sy, sz, pos, dist, n, c->tree.pts, c->d_state, mask_out, part);
-    stage_b_reduce_kernel<<<1, RED_THREADS, 0, c->stream>>>(part, blocks, rank_part_slot);
-    c->launches += 2;
+    stage_b_kernel<<<blocks, RED_THREADS, 0, c->stream>>>(sx, sy, sz, pos, dist, n, c->tree.pts, c->d_state, rank_a, c->n_ranks,
+                                                          c->rank, iter, mask_out, part, rank_b, c->d_rec);
+    c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
     return ICP_OK;
 }
@@ -472,13 +568,11 @@ __device__ __forceinline__ void moments_to_H(const double* b17, const double* pa
 }
 
 // Sums the rank partials in rank order, then RMSE, loop control and the Kabsch solve.
-__global__ void solve_kernel(LoopState* __restrict__ st, const double* __restrict__ rank_parts, int n_ranks,
-                             IterRecord* __restrict__ rec) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __noinline__ void solve_step(LoopState* st, const double* rank_parts, int n_ranks, IterRecord* rec) {
     double b[STATB_DOUBLES];
     for (int k = 0; k < STATB_DOUBLES; ++k) {
-        double v = rank_parts[k];
-        for (int r = 1; r < n_ranks; ++r) v += rank_parts[(int64_t)r * STATB_DOUBLES + k];
+        double v = __ldcg(rank_parts + k);
+        for (int r = 1; r < n_ranks; ++r) v += __ldcg(rank_parts + (int64_t)r * STATB_DOUBLES + k);
         b[k] = v;
     }
     const double valid = b[0];
@@ -533,6 +627,12 @@ __global__ void solve_kernel(LoopState* __restrict__ st, const double* __restric
         rec->T_last[i] = st->T_last[i];
     }
     __threadfence_system();
+}
+
+__global__ void solve_kernel(LoopState* __restrict__ st, const double* __restrict__ rank_parts, int n_ranks,
+                             IterRecord* __restrict__ rec) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    solve_step(st, rank_parts, n_ranks, rec);
 }
 
 int solve_launch(Ctx* c, const double* rank_parts, int n_ranks) {

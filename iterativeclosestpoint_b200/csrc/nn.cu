@@ -43,6 +43,8 @@ struct NNArgs {
     uint32_t* pos_out;
     double* dist_out;
     const uint32_t* prev_pos;  // last iteration's match per query (may be null)
+    uint32_t* node_io;         // in: leaf that held last iteration's match; out: this iteration's (may be null)
+    const uint32_t* __restrict__ parent;
     StatA* part_a;
     const LoopState* state;
     unsigned long long* counters;  // [0] queries answered by the fast path, [1] literal fallbacks (may be null)
@@ -211,15 +213,16 @@ __device__ __forceinline__ void dfs_literal(const Node* __restrict__ nodes, cons
 // ---------------------------------------------------------------------------------------------------
 struct Fast {
     double best, second, bound;
-    uint32_t pos;
+    uint32_t pos, node;
 };
 
-__device__ __forceinline__ void fast_take(Fast& F, double s, uint32_t pos) {
+__device__ __forceinline__ void fast_take(Fast& F, double s, uint32_t pos, uint32_t node) {
     const double grow = 1.0 + 1.8189894035458565e-12;  // 1 + 2^-39
     if (s < F.best) {
         F.second = F.best;
         F.best = s;
         F.pos = pos;
+        F.node = node;
         const double b = dmul(s, grow);
         F.bound = b < F.bound ? b : F.bound;
     } else if (s < F.second) {
@@ -243,7 +246,7 @@ __device__ __forceinline__ void fast_search(const Node* __restrict__ nodes, cons
                     double px, py, pz;
                     uint32_t pidx;
                     load_point(pts, nd.pt0 + k, px, py, pz, pidx);
-                    fast_take(F, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)), nd.pt0 + k);
+                    fast_take(F, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)), nd.pt0 + k, cur);
                 }
             }
         } else {
@@ -336,60 +339,100 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
             A.oz[i] = qz;
         }
         const bool finite_q = isfinite(qx) && isfinite(qy) && isfinite(qz);
-        uint32_t result = NONE;
+        uint32_t result = NONE, result_node = NONE;
         bool need_literal = finite_q;
         if (A.mode == 1 && finite_q) {
-            // ---- point location: walk down the cell path of q, remembering each level's clearance ----
-            uint32_t n = 0;
-            int level = 0;
-            NodeRegs nd;
-            // Running pointer rather than stk[level * NN_THREADS]: ptxas 12.9 (sm_100a) mis-addressed the indexed
-            // form of this store by two rows in the rotated loop (seen in SASS and on the device), PTX was correct.
-            uint2* path = stk;
-            for (;;) {
-                nd = load_node(A.nodes, n);
-                double c = fmin(fmin(dsub(qx, nd.lo[0]), dsub(nd.hi[0], qx)),
-                                fmin(fmin(dsub(qy, nd.lo[1]), dsub(nd.hi[1], qy)), fmin(dsub(qz, nd.lo[2]), dsub(nd.hi[2], qz))));
-                float cf = (c > 0.0) ? __double2float_rd(c) : 0.0f;
-                *path = make_uint2(n, __float_as_uint(cf));
-                const uint32_t mask = nd.meta & 0xFFu;
-                if (mask == 0) break;
-                uint32_t oct = 0;
-                oct |= (qx > dmul(dadd(nd.lo[0], nd.hi[0]), 0.5)) ? 1u : 0u;
-                oct |= (qy > dmul(dadd(nd.lo[1], nd.hi[1]), 0.5)) ? 2u : 0u;
-                oct |= (qz > dmul(dadd(nd.lo[2], nd.hi[2]), 0.5)) ? 4u : 0u;
-                if (!((mask >> oct) & 1u)) break;
-                n = nd.child0 + __popc(mask & ((1u << oct) - 1u));
-                ++level;
-                path += NN_THREADS;
-            }
-            // ---- seed: squared distance of a real target point ----
             double Sd = ICPB_INF;
-            const uint32_t ns = nd.npts < (uint32_t)SEED_SCAN ? nd.npts : (uint32_t)SEED_SCAN;
-            for (uint32_t k = 0; k < ns; ++k) {
-                double px, py, pz;
-                uint32_t pidx;
-                load_point(A.pts, nd.pt0 + k, px, py, pz, pidx);
-                Sd = fmin(Sd, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)));
+            uint32_t start = 0;
+            uint32_t pp = NONE, pn = NONE;
+            if (A.prev_pos && A.node_io) {
+                pp = A.prev_pos[i];
+                pn = A.node_io[i];
             }
-            if (A.prev_pos) {
-                const uint32_t pp = A.prev_pos[i];
+            if (pp != NONE && pn != NONE) {
+                // ---- temporal start: last iteration's match seeds the bound, its leaf seeds the start node ----
+                {
+                    double px, py, pz;
+                    uint32_t pidx;
+                    load_point(A.pts, pp, px, py, pz, pidx);
+                    Sd = sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz));
+                }
+                const double clear_req = dmul(Sd, 1.0 + 3.637978807091713e-12);  // S (1 + 2^-38)
+                uint32_t n = pn;
+                NodeRegs nd;
+                bool inside_first = false, first = true;
+                for (;;) {  // climb until the query sits inside with enough clearance (the root always qualifies)
+                    nd = load_node(A.nodes, n);
+                    const double c = fmin(fmin(dsub(qx, nd.lo[0]), dsub(nd.hi[0], qx)),
+                                          fmin(fmin(dsub(qy, nd.lo[1]), dsub(nd.hi[1], qy)), fmin(dsub(qz, nd.lo[2]), dsub(nd.hi[2], qz))));
+                    const double cf = (c > 0.0) ? (double)__double2float_rd(c) : 0.0;
+                    if (first) inside_first = c >= 0.0;
+                    first = false;
+                    if (cf * cf > clear_req || n == 0u) break;
+                    n = __ldg(A.parent + n);
+                }
+                if (!inside_first) {
+                    // the query left last iteration's leaf: walk back down its own cell path while clearance allows
+                    for (;;) {
+                        const uint32_t mask = nd.meta & 0xFFu;
+                        if (mask == 0) break;
+                        uint32_t oct = 0;
+                        oct |= (qx > dmul(dadd(nd.lo[0], nd.hi[0]), 0.5)) ? 1u : 0u;
+                        oct |= (qy > dmul(dadd(nd.lo[1], nd.hi[1]), 0.5)) ? 2u : 0u;
+                        oct |= (qz > dmul(dadd(nd.lo[2], nd.hi[2]), 0.5)) ? 4u : 0u;
+                        if (!((mask >> oct) & 1u)) break;
+                        const uint32_t ch = nd.child0 + __popc(mask & ((1u << oct) - 1u));
+                        const NodeRegs cd = load_node(A.nodes, ch);
+                        const double c = fmin(fmin(dsub(qx, cd.lo[0]), dsub(cd.hi[0], qx)),
+                                              fmin(fmin(dsub(qy, cd.lo[1]), dsub(cd.hi[1], qy)), fmin(dsub(qz, cd.lo[2]), dsub(cd.hi[2], qz))));
+                        const double cf = (c > 0.0) ? (double)__double2float_rd(c) : 0.0;
+                        if (!(cf * cf > clear_req)) break;
+                        n = ch;
+                        nd = cd;
+                    }
+                }
+                start = n;
+            } else {
+                // ---- point location: walk down the cell path of q, remembering each level's clearance ----
+                uint32_t n = 0;
+                int level = 0;
+                NodeRegs nd;
+                // Running pointer rather than stk[level * NN_THREADS]: ptxas 12.9 (sm_100a) mis-addressed the indexed
+                // form of this store by two rows in the rotated loop (seen in SASS and on the device), PTX was correct.
+                uint2* path = stk;
+                for (;;) {
+                    nd = load_node(A.nodes, n);
+                    double c = fmin(fmin(dsub(qx, nd.lo[0]), dsub(nd.hi[0], qx)),
+                                    fmin(fmin(dsub(qy, nd.lo[1]), dsub(nd.hi[1], qy)), fmin(dsub(qz, nd.lo[2]), dsub(nd.hi[2], qz))));
+                    float cf = (c > 0.0) ? __double2float_rd(c) : 0.0f;
+                    *path = make_uint2(n, __float_as_uint(cf));
+                    const uint32_t mask = nd.meta & 0xFFu;
+                    if (mask == 0) break;
+                    uint32_t oct = 0;
+                    oct |= (qx > dmul(dadd(nd.lo[0], nd.hi[0]), 0.5)) ? 1u : 0u;
+                    oct |= (qy > dmul(dadd(nd.lo[1], nd.hi[1]), 0.5)) ? 2u : 0u;
+                    oct |= (qz > dmul(dadd(nd.lo[2], nd.hi[2]), 0.5)) ? 4u : 0u;
+                    if (!((mask >> oct) & 1u)) break;
+                    n = nd.child0 + __popc(mask & ((1u << oct) - 1u));
+                    ++level;
+                    path += NN_THREADS;
+                }
+                // ---- seed: squared distance of a real target point of the located cell ----
+                const uint32_t ns = nd.npts < (uint32_t)SEED_SCAN ? nd.npts : (uint32_t)SEED_SCAN;
+                for (uint32_t k = 0; k < ns; ++k) {
+                    double px, py, pz;
+                    uint32_t pidx;
+                    load_point(A.pts, nd.pt0 + k, px, py, pz, pidx);
+                    Sd = fmin(Sd, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)));
+                }
                 if (pp != NONE) {
                     double px, py, pz;
                     uint32_t pidx;
                     load_point(A.pts, pp, px, py, pz, pidx);
                     Sd = fmin(Sd, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)));
                 }
-            }
-            if (Sd < 1e19) {  // also false for inf/NaN; keeps clear of the CLI's initial best 1e20
-                Fast F;
-                F.best = ICPB_INF;
-                F.second = ICPB_INF;
-                F.pos = NONE;
-                F.bound = dmul(Sd, 1.0 + 1.8189894035458565e-12);                // S (1 + 2^-39)
-                const double clear_req = dmul(Sd, 1.0 + 3.637978807091713e-12);  // S (1 + 2^-38)
                 // ---- subtree start: deepest path node whose clearance^2 exceeds the seed bound ----
-                uint32_t start = 0;
+                const double clear_req = dmul(Sd, 1.0 + 3.637978807091713e-12);  // S (1 + 2^-38)
                 for (int l = level; l > 0; --l) {
                     const uint2 e = *path;
                     path -= NN_THREADS;
@@ -399,10 +442,19 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
                         break;
                     }
                 }
+            }
+            if (Sd < 1e19) {  // also false for inf/NaN; keeps clear of the CLI's initial best 1e20
+                Fast F;
+                F.best = ICPB_INF;
+                F.second = ICPB_INF;
+                F.pos = NONE;
+                F.node = NONE;
+                F.bound = dmul(Sd, 1.0 + 1.8189894035458565e-12);                // S (1 + 2^-39)
                 fast_search(A.nodes, A.pts, qx, qy, qz, start, F, stk);
                 // unique minimum with margin 2^-40 => order-independent => the reference's answer
                 if (F.pos != NONE && F.second > dmul(F.best, 1.0 + 9.094947017729282e-13)) {
                     result = F.pos;
+                    result_node = F.node;
                     need_literal = false;
                 }
             }
@@ -428,6 +480,7 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
         // computeDistance(p_src, p_tgt) (icpengine.cpp:68-74)
         const double d = dsqrt(sumsq3(dsub(qx, px), dsub(qy, py), dsub(qz, pz)));
         A.pos_out[i] = pos;
+        if (A.node_io) A.node_io[i] = result_node;
         A.dist_out[i] = d;
         st.n = 1.0;
         st.mean = d;
@@ -472,6 +525,8 @@ int nn_launch(Ctx* c, const NNLaunch& L) {
     A.pos_out = L.pos_out;
     A.dist_out = L.dist_out;
     A.prev_pos = L.prev_pos;
+    A.node_io = L.node_io;
+    A.parent = c->tree.parent;
     A.part_a = L.part_a;
     A.state = L.state;
     A.counters = c->d_counters;

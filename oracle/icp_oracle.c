@@ -542,7 +542,9 @@ void orc_mat4_mul(const double* A, const double* B, double* C) {
 void orc_angles(const double* T, double* angle_deg, double* trans_dist) {
     double trace = T[0] + (T[5] + T[10]);
     *angle_deg = acos((trace - 1.0) / 2.0) * 180.0 / M_PI;
-    *trans_dist = sqrt(T[3] * T[3] + (T[7] * T[7] + T[11] * T[11]));
+    /* Block<Matrix4d,3,1>::norm(): vectorised redux, packet (t0,t1) first, then the scalar tail -- pinned by
+     * tests/golden/engine_*.npz (the trace above is the unrolled scalar redux a0 + (a1 + a2)) */
+    *trans_dist = sqrt((T[3] * T[3] + T[7] * T[7]) + T[11] * T[11]);
 }
 
 /* ------------------------------------------------------------------------------------------------------
