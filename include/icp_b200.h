@@ -122,8 +122,10 @@ int icp_get_params(icp_handle h, icp_params* p);                /* ICPEngine::ge
 void icp_default_params(icp_params* p);                         /* ICPParameters defaults (icpengine.h:13-19) */
 int icp_set_callbacks(icp_handle h, icp_iteration_cb on_iteration, icp_progress_cb on_progress, icp_log_cb on_log,
                       void* user);
-/* Tuning knobs that never change results: "nn_mode" (0 = literal root traversal, 1 = fast path with literal fallback, default),
- * "order_queries" (Morton-order the source internally, default 1), "write_mask" (keep the inlier mask). */
+/* Tuning knobs that never change results: "nn_mode" (0 = literal reference traversal from the root, one query per
+ * thread; 1 = per-thread order-independent search with literal fallback; 2 = warp tiles with shared-memory staged
+ * candidates, per-thread and literal fallbacks -- the default), "order_queries" (Morton-order the source internally,
+ * default 1), "write_mask" (keep the inlier mask). */
 int icp_set_option(icp_handle h, const char* key, double value);
 
 /* ---- the whole hot path, HOST buffers in and out ------------------------------------------------- */
@@ -183,6 +185,9 @@ int icp_register_batch(icp_handle h, int32_t n_pairs, double* const* src_xyz, co
 /* How many queries since the last reset were answered by the order-independent fast path and how many
  * had to be re-run through the literal reference traversal (exact ties / duplicates / 1-ulp near ties). */
 int icp_nn_counters(icp_handle h, int64_t* fast_path, int64_t* literal_fallback, int reset);
+/* Tile kernel (nn_mode 2): lanes a tile could not prove and handed to the per-thread search, and the number of
+ * (tile, candidate) pairs scanned -- candidates per query = candidates_scanned / queries. */
+int icp_nn_tile_counters(icp_handle h, int64_t* per_thread_lanes, int64_t* candidates_scanned, int reset);
 
 /* Number of kernels this library has launched on the handle since creation (bench.py's gpu_launches). */
 int64_t icp_kernel_launches(icp_handle h);

@@ -32,7 +32,7 @@ EXPORTED = [
     "icp_register_resident", "icp_octree_build", "icp_octree_get_info", "icp_octree_dump", "icp_nn_query",
     "icp_iteration_stats", "icp_best_fit_transform", "icp_solve_from_H", "icp_apply_transform",
     "icp_comm_unique_id", "icp_comm_init", "icp_comm_destroy", "icp_register_sharded", "icp_register_batch",
-    "icp_kernel_launches", "icp_nn_counters",
+    "icp_kernel_launches", "icp_nn_counters", "icp_nn_tile_counters",
 ]
 
 
@@ -124,6 +124,7 @@ def load() -> C.CDLL:
     L.icp_register_sharded.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.c_int64, C.POINTER(IcpResult), vp]
     L.icp_register_batch.argtypes = [vp, C.c_int32, vp, vp, vp, vp, C.POINTER(IcpResult)]
     L.icp_nn_counters.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
+    L.icp_nn_tile_counters.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
     L.icp_kernel_launches.argtypes = [vp]
     L.icp_kernel_launches.restype = C.c_int64
     _lib = L

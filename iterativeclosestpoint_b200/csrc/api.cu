@@ -139,6 +139,7 @@ static int upload(Ctx* c, DevBuf& stage, const double* host_xyz, int64_t n) {
 }
 
 static int source_from_device_aos(Ctx* c, const double* d_xyz, int64_t n) {
+    c->prev_valid = false;
     ICPB_TRY(ensure_source_buffers(c, n));
     c->n_src = n;
     if (c->opt_order_queries && n > 1)
@@ -187,6 +188,10 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     double* part_b = (double*)c->part_b.p;
     const double init_best = (variant == ICP_VARIANT_CLI) ? 1e20 : DBL_MAX;  // octree.cpp:180 vs icp_registration.cpp:201
 
+    const bool resume = c->prev_valid;  // same resident source and tree as the last run: its matches seed this one
+    c->prev_valid = false;
+    if (c->opt_nn_mode == 2 && !resume)  // per-tile start nodes: the root until a tile has searched once
+        ICPB_CUDA(c, cudaMemsetAsync(c->node_io.p, 0, (size_t)((n + 31) / 32) * sizeof(uint32_t), c->stream));
     ICPB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     for (int iter = 0; iter < P.max_iterations; ++iter) {
         if (variant == ICP_VARIANT_ENGINE && stop_flag && *stop_flag) {  // icpengine.cpp:160-164
@@ -204,8 +209,9 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         L.n = n;
         L.pos_out = (uint32_t*)c->pos.p;
         L.dist_out = (double*)c->dist.p;
-        L.prev_pos = (iter > 0 && c->opt_nn_mode == 1) ? (uint32_t*)c->pos.p : nullptr;
+        L.prev_pos = ((iter > 0 || resume) && c->opt_nn_mode >= 1) ? (uint32_t*)c->pos.p : nullptr;
         L.node_io = (c->opt_nn_mode == 1) ? (uint32_t*)c->node_io.p : nullptr;
+        L.tile_node = (c->opt_nn_mode == 2) ? (uint32_t*)c->node_io.p : nullptr;
         L.part_a = nullptr;
         L.state = c->d_state;
         L.apply_pending = 1;
@@ -292,6 +298,7 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     out->history_len = std::min(n_hist, out->history ? out->history_cap : 0);
     std::memcpy(out->cumulative_T, T_cum, sizeof T_cum);
     std::memcpy(out->last_T, T_last, sizeof T_last);
+    c->prev_valid = out->loop_iterations > 0 && c->opt_nn_mode >= 1;
     if (*write_back) {
         ICPB_TRY(apply_pending_launch(c, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p, n));  // the last T, if any
         out->success = 1;
@@ -428,12 +435,13 @@ int icp_create(icp_handle* out, int device_id) {
     for (auto& e : c->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaMalloc(&c->d_state, sizeof(LoopState)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
-    if (cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
-    cudaMemset(c->d_counters, 0, 2 * sizeof(unsigned long long));
+    if (cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long));
     if (cudaHostAlloc(&c->h_rec, sizeof(IterRecord), cudaHostAllocMapped) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaHostGetDevicePointer(&c->d_rec, c->h_rec, 0) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    if (getenv("ICP_B200_DEBUG_COUNTERS")) c->opt_count = true;
     const char* m = getenv("ICP_B200_NN_MODE");
-    if (m) c->opt_nn_mode = atoi(m) ? 1 : 0;
+    if (m) c->opt_nn_mode = std::min(std::max(atoi(m), 0), 2);
     *out = (icp_handle)c;
     return ICP_OK;
 }
@@ -498,7 +506,12 @@ int icp_set_callbacks(icp_handle h, icp_iteration_cb on_iteration, icp_progress_
 int icp_set_option(icp_handle h, const char* key, double value) {
     Ctx* c = (Ctx*)h;
     if (!c || !key) return ICP_INVALID_ARGUMENT;
-    if (!strcmp(key, "nn_mode")) c->opt_nn_mode = value != 0.0 ? 1 : 0;
+    if (!strcmp(key, "nn_mode")) {
+        c->opt_nn_mode = value < 0.5 ? 0 : (value < 1.5 ? 1 : 2);
+        c->prev_valid = false;
+    }
+    else if (!strcmp(key, "count")) c->opt_count = value != 0.0;
+    else if (!strcmp(key, "search_leaf")) c->opt_search_leaf = std::min(std::max((int)value, 1), 1024);
     else if (!strcmp(key, "order_queries")) c->opt_order_queries = value != 0.0;
     else if (!strcmp(key, "write_mask")) c->opt_write_mask = value != 0.0;
     else {
@@ -512,12 +525,31 @@ int icp_nn_counters(icp_handle h, int64_t* fast_path, int64_t* literal_fallback,
     Ctx* c = (Ctx*)h;
     if (!c) return ICP_INVALID_ARGUMENT;
     ICPB_CUDA(c, cudaSetDevice(c->device));
-    unsigned long long v[2] = {0, 0};
+    unsigned long long v[4] = {0, 0, 0, 0};
     ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
     ICPB_CUDA(c, cudaMemcpy(v, c->d_counters, sizeof v, cudaMemcpyDeviceToHost));
     if (fast_path) *fast_path = (int64_t)v[0];
     if (literal_fallback) *literal_fallback = (int64_t)v[1];
-    if (reset) ICPB_CUDA(c, cudaMemset(c->d_counters, 0, sizeof v));
+    if (reset) ICPB_CUDA(c, cudaMemset(c->d_counters, 0, 2 * sizeof(unsigned long long)));
+    return ICP_OK;
+}
+
+int icp_nn_tile_counters(icp_handle h, int64_t* per_thread_lanes, int64_t* candidates_scanned, int reset) {
+    Ctx* c = (Ctx*)h;
+    if (!c) return ICP_INVALID_ARGUMENT;
+    ICPB_CUDA(c, cudaSetDevice(c->device));
+    unsigned long long v[4] = {0, 0, 0, 0};
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    ICPB_CUDA(c, cudaMemcpy(v, c->d_counters, sizeof v, cudaMemcpyDeviceToHost));
+    if (per_thread_lanes) *per_thread_lanes = (int64_t)v[2];
+    if (candidates_scanned) *candidates_scanned = (int64_t)v[3];
+    if (getenv("ICP_B200_DEBUG_COUNTERS")) {
+        unsigned long long w[8];
+        ICPB_CUDA(c, cudaMemcpy(w, c->d_counters, sizeof w, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[icp_b200] tile counters: slow_lanes=%llu candidates=%llu rounds=%llu passes=%llu nodes=%llu start_steps=%llu\n", w[2], w[3],
+                w[4], w[5], w[6], w[7]);
+    }
+    if (reset) ICPB_CUDA(c, cudaMemset(c->d_counters + 2, 0, 6 * sizeof(unsigned long long)));
     return ICP_OK;
 }
 
@@ -675,6 +707,7 @@ int icp_iteration_stats(icp_handle h, const double* src_xyz, int64_t n, const in
     if (!src_xyz || !idx || n <= 0) return ICP_EMPTY_INPUT;
     ICPB_CUDA(c, cudaSetDevice(c->device));
     ICPB_TRY(build_inv_perm(c));
+    c->prev_valid = false;
     ICPB_TRY(upload(c, c->scratch_src, src_xyz, n));
     ICPB_TRY(ensure_source_buffers(c, n));
     ICPB_TRY(ensure_run_buffers(c, n));

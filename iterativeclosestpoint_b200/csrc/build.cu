@@ -191,6 +191,13 @@ __global__ void bbox_finish_kernel(const double* __restrict__ part, int n_part, 
     root[a] = (a < 3) ? dsub(v, eps) : dadd(v, eps);  // octree.cpp:61-64
 }
 
+// Search tree only: make the root a cube (one edge length for all axes) so that its cells are isotropic.
+__global__ void cube_root_kernel(double* __restrict__ root) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double ext = fmax(fmax(root[3] - root[0], root[4] - root[1]), root[5] - root[2]) * (1.0 + 1e-12);
+    for (int a = 0; a < 3; ++a) root[3 + a] = fmax(root[3 + a], root[a] + ext);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1: octant-path keys by FP64 bisection (octree.cpp:97-110 applied max_depth times)
 // ------------------------------------------------------------------------------------------------
@@ -453,8 +460,7 @@ __global__ void inv_perm_kernel(const TPoint* __restrict__ pts, int64_t n, uint3
     if (i < n) inv[(uint32_t)pts[i].idx] = (uint32_t)i;
 }
 
-void octree_free(Ctx* c) {
-    DeviceOctree& t = c->tree;
+static void tree_free(DeviceOctree& t) {
     if (t.nodes) cudaFree(t.nodes);
     if (t.parent) cudaFree(t.parent);
     if (t.pts) cudaFree(t.pts);
@@ -462,8 +468,12 @@ void octree_free(Ctx* c) {
     t = DeviceOctree();
 }
 
-static int grow_nodes(Ctx* c, int64_t need) {
-    DeviceOctree& t = c->tree;
+void octree_free(Ctx* c) {
+    tree_free(c->tree);
+    tree_free(c->fast);
+}
+
+static int grow_nodes(Ctx* c, DeviceOctree& t, int64_t need) {
     if (need <= t.cap_nodes) return ICP_OK;
     int64_t cap = std::max<int64_t>(need + need / 2, 1024);
     Node* nn = nullptr;
@@ -483,14 +493,12 @@ static int grow_nodes(Ctx* c, int64_t need) {
     return ICP_OK;
 }
 
-int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int max_depth) {
-    octree_free(c);
-    if (m <= 0) return ICP_EMPTY_INPUT;
-    if (max_depth < 0 || max_depth > 21 || m > 0x7fffffffLL) {
-        c->err = "octree: max_depth must be in [0,21] and n_tgt < 2^31";
-        return ICP_INVALID_ARGUMENT;
-    }
-    DeviceOctree& t = c->tree;
+// Builds one linear octree over the m target points at d_xyz.  cubic == false: the reference's tree (root = the
+// cloud's bounding box, octree.cpp:41-126).  cubic == true: the SEARCH tree -- same construction over a cubic root,
+// so its cells are cubes; it only has to bound its points (every point lies in the closed box of its leaf), not
+// to match anything in the reference.
+static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, int max_pts, int max_depth, bool cubic) {
+    tree_free(t);
     t.max_pts = max_pts;
     t.max_depth = max_depth;
     t.n_pts = m;
@@ -504,6 +512,10 @@ int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int
     bbox_partial_kernel<<<bb_blocks, BBOX_THREADS, 0, s>>>(d_xyz, m, d_part);
     bbox_finish_kernel<<<1, 32, 0, s>>>(d_part, bb_blocks, d_xyz, d_root);
     c->launches += 2;
+    if (cubic) {
+        cube_root_kernel<<<1, 32, 0, s>>>(d_root);
+        c->launches++;
+    }
 
     // K1
     uint64_t *keys = nullptr, *keys_alt = nullptr;
@@ -531,7 +543,7 @@ int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int
     c->launches++;
 
     // K3
-    ICPB_TRY(grow_nodes(c, std::max<int64_t>(m / 2, 1024)));
+    ICPB_TRY(grow_nodes(c, t, std::max<int64_t>(m / 2, 1024)));
     ICPB_CUDA(c, cudaMemsetAsync(t.parent, 0xFF, sizeof(uint32_t), s));
     root_node_kernel<<<1, 32, 0, s>>>(t.nodes, d_root, (uint32_t)m);
     c->launches++;
@@ -549,7 +561,7 @@ int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int
         ICPB_CUDA(c, cudaMemcpyAsync(&n_children, d_misc + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         ICPB_CUDA(c, cudaStreamSynchronize(s));
         const uint32_t next_first = first + count;
-        ICPB_TRY(grow_nodes(c, (int64_t)next_first + n_children));
+        ICPB_TRY(grow_nodes(c, t, (int64_t)next_first + n_children));
         node_emit_kernel<<<nb, 128, 0, s>>>(t.nodes, first, count, keys, level, max_pts, max_depth, offs, next_first,
                                             d_misc + 1, t.parent);
         c->launches++;
@@ -575,6 +587,31 @@ int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int
     return ICP_OK;
 }
 
+static int build_inv_perm_of(Ctx* c, DeviceOctree& t) {
+    if (t.inv_perm) return ICP_OK;
+    ICPB_CUDA(c, cudaMalloc(&t.inv_perm, (size_t)t.n_pts * sizeof(uint32_t)));
+    inv_perm_kernel<<<(int)((t.n_pts + 255) / 256), 256, 0, c->stream>>>(t.pts, t.n_pts, t.inv_perm);
+    c->launches++;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
+// The reference's tree (c->tree: structure parity, literal traversal) and the isotropic search tree (c->fast: every
+// fast search path, and the canonical point order that match positions refer to).
+int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int max_depth) {
+    octree_free(c);
+    c->prev_valid = false;
+    if (m <= 0) return ICP_EMPTY_INPUT;
+    if (max_depth < 0 || max_depth > 21 || m > 0x7fffffffLL) {
+        c->err = "octree: max_depth must be in [0,21] and n_tgt < 2^31";
+        return ICP_INVALID_ARGUMENT;
+    }
+    ICPB_TRY(build_tree(c, c->tree, d_xyz, m, max_pts, max_depth, false));
+    ICPB_TRY(build_tree(c, c->fast, d_xyz, m, c->opt_search_leaf, 21, true));
+    ICPB_TRY(build_inv_perm_of(c, c->fast));  // original index -> search-tree position (literal results, stage API)
+    return ICP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Query ordering: the NN kernel runs one query per thread, so neighbouring threads should walk the same
 // nodes.  Queries are ordered by a 3x21-bit Morton code of their own bounding box (this is only a
@@ -585,15 +622,19 @@ __global__ void __launch_bounds__(256) query_keys_kernel(const double* __restric
                                                          uint32_t* __restrict__ idx) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    // ISOTROPIC cells: one scale (the largest extent) for all three axes, so that 32 consecutive queries form a
+    // compact, roughly cubic clump (a per-axis scale would slice 2.5-D scenes into thin height slabs whose tiles
+    // follow contour lines).
+    const double ext = fmax(fmax(box[3] - box[0], box[4] - box[1]), box[5] - box[2]);
+    const double inv = ext > 0.0 ? 2097151.0 / ext : 0.0;
     uint64_t key = 0;
     uint32_t q[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const double lo = box[a], hi = box[3 + a];
-        double f = (xyz[3 * i + a] - lo) / (hi - lo);
+        double f = (xyz[3 * i + a] - box[a]) * inv;
         if (!(f > 0.0)) f = 0.0;  // also catches NaN
-        if (f > 1.0) f = 1.0;
-        q[a] = (uint32_t)(f * 2097151.0);
+        if (f > 2097151.0) f = 2097151.0;
+        q[a] = (uint32_t)f;
     }
     for (int b = 20; b >= 0; --b)
         key = (key << 3) | (((q[0] >> b) & 1u)) | (((q[1] >> b) & 1u) << 1) | (((q[2] >> b) & 1u) << 2);
@@ -636,14 +677,6 @@ int order_queries(Ctx* c, const double* d_q, int64_t n, double* sx, double* sy, 
     return ICP_OK;
 }
 
-int build_inv_perm(Ctx* c) {
-    DeviceOctree& t = c->tree;
-    if (t.inv_perm) return ICP_OK;
-    ICPB_CUDA(c, cudaMalloc(&t.inv_perm, (size_t)t.n_pts * sizeof(uint32_t)));
-    inv_perm_kernel<<<(int)((t.n_pts + 255) / 256), 256, 0, c->stream>>>(t.pts, t.n_pts, t.inv_perm);
-    c->launches++;
-    ICPB_CUDA(c, cudaGetLastError());
-    return ICP_OK;
-}
+int build_inv_perm(Ctx* c) { return build_inv_perm_of(c, c->fast); }
 
 }  // namespace icpb

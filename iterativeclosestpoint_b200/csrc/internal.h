@@ -45,7 +45,9 @@ struct Ctx {
     int64_t launches = 0;
     int sm_count = 148;
 
-    DeviceOctree tree;
+    DeviceOctree tree;  // the reference's octree (structure parity, literal traversal)
+    DeviceOctree fast;  // isotropic search tree over the same points; match positions index ITS point order
+    int opt_search_leaf = 16;        // leaf capacity of the search tree
     DevBuf tgt_raw;  // original-order target AoS (kept for the stage API)
     int64_t n_tgt = 0;
 
@@ -57,13 +59,15 @@ struct Ctx {
     DevBuf part_a, part_b;     // per-block partials
     DevBuf scratch0, scratch1, scratch2, scratch3, scratch_src;
     bool src_identity_perm = false;  // resident source is in caller order (no permutation)
+    bool prev_valid = false;         // pos / node_io hold last run's matches of the resident source against the current tree
     float last_build_ms = 0.f;
     // tuning knobs (icp_set_option)
-    int opt_nn_mode = 1;             // 0: literal traversal from the root; 1: seeded + subtree start
+    int opt_nn_mode = 2;             // 0: literal traversal from the root; 1: per-thread fast path; 2: warp tiles
     bool opt_order_queries = true;   // Morton-order the source for traversal coherence
     bool opt_write_mask = false;     // keep the per-point inlier mask of the last iteration
+    bool opt_count = false;          // maintain the NN path counters (same-address atomics: profiling / tests only)
     LoopState* d_state = nullptr;
-    unsigned long long* d_counters = nullptr;  // [0] fast-path answers, [1] literal fallbacks
+    unsigned long long* d_counters = nullptr;  // see NNArgs::counters (4 entries)
     IterRecord* h_rec = nullptr;  // pinned, device-mapped
     IterRecord* d_rec = nullptr;
 
@@ -115,10 +119,11 @@ struct NNLaunch {
     double* dist_out;      // distance
     const uint32_t* prev_pos;  // last iteration's match per query, seeds the search (may be null)
     uint32_t* node_io;         // in: node the previous search started from; out: this one's (may be null)
+    uint32_t* tile_node = nullptr;  // mode 2: per-tile start node of the last search (may be null)
     StatA* part_a;         // per-block partial (may be null: no statistics)
     const LoopState* state;  // may be null (stateless query)
     int apply_pending;     // read state->have_T / T_pending and transform on load
-    int mode;              // 0: literal traversal from the root; 1: seeded + subtree start
+    int mode;              // 0: literal traversal from the root; 1: per-thread fast path; 2: warp tiles
     double init_best;      // DBL_MAX (engine) or 1e20 (CLI)
 };
 int nn_launch(Ctx* c, const NNLaunch& L);

@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(RED_THREADS) dist_from_idx_kernel(const double
 int dist_from_idx_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const int32_t* idx, int64_t n,
                          uint32_t* pos_out, double* dist_out, StatA* part, int* n_part) {
     const int blocks = (int)std::min<int64_t>((n + RED_THREADS - 1) / RED_THREADS, (int64_t)c->sm_count * 4);
-    dist_from_idx_kernel<<<blocks, RED_THREADS, 0, c->stream>>>(sx, sy, sz, idx, n, c->tree.inv_perm, c->tree.n_pts,
-                                                                c->tree.pts, c->params.variant, pos_out, dist_out, part);
+    dist_from_idx_kernel<<<blocks, RED_THREADS, 0, c->stream>>>(sx, sy, sz, idx, n, c->fast.inv_perm, c->fast.n_pts,
+                                                                c->fast.pts, c->params.variant, pos_out, dist_out, part);
     c->launches++;
     *n_part = blocks;
     ICPB_CUDA(c, cudaGetLastError());
@@ -364,7 +364,7 @@ int stage_b_blocks(Ctx* c, int64_t n) {
 int stage_b_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const uint32_t* pos, const double* dist,
                    int64_t n, int iter, const StatA* rank_a, uint8_t* mask_out, double* part, double* rank_b) {
     const int blocks = stage_b_blocks(c, n);
-    stage_b_kernel<<<blocks, RED_THREADS, 0, c->stream>>>(sx, sy, sz, pos, dist, n, c->tree.pts, c->d_state, rank_a, c->n_ranks,
+    stage_b_kernel<<<blocks, RED_THREADS, 0, c->stream>>>(sx, sy, sz, pos, dist, n, c->fast.pts, c->d_state, rank_a, c->n_ranks,
                                                           c->rank, iter, mask_out, part, rank_b, c->d_rec);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
@@ -774,7 +774,7 @@ int unsort_launch(Ctx* c, const double* sx, const double* sy, const double* sz, 
 
 int unsort_results_launch(Ctx* c, const uint32_t* pos, const double* dist, const uint32_t* perm, int64_t n, int32_t* idx_out,
                           double* dist_out) {
-    unsort_results_kernel<<<nblk(n), 256, 0, c->stream>>>(pos, dist, perm, c->tree.pts, n, idx_out, dist_out);
+    unsort_results_kernel<<<nblk(n), 256, 0, c->stream>>>(pos, dist, perm, c->fast.pts, n, idx_out, dist_out);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
     return ICP_OK;

@@ -1,0 +1,441 @@
+// Device-side pieces shared by the NN kernels (nn.cu: one query per thread; nn_tile.cu: one tile of queries per warp).
+#pragma once
+#include "internal.h"
+
+namespace icpb {
+
+
+constexpr int NN_MAX_LEVELS = 22;           // octree_max_depth <= 21  => at most 22 levels on a path
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr int SEED_SCAN = 8;                // points inspected to seed a query
+#define ICPB_INF __longlong_as_double(0x7FF0000000000000LL)
+
+struct NNArgs {
+    const Node* __restrict__ nodes;    // search tree (isotropic cells): every fast path; match positions index `pts`
+    const TPoint* __restrict__ pts;
+    const Node* __restrict__ rnodes;   // the reference's octree and its point order: literal traversal only
+    const TPoint* __restrict__ rpts;
+    const uint32_t* __restrict__ inv;  // original target index -> position in `pts`
+    const double* sx;
+    const double* sy;
+    const double* sz;
+    double* ox;
+    double* oy;
+    double* oz;
+    long long n;
+    uint32_t* pos_out;
+    double* dist_out;
+    const uint32_t* prev_pos;  // last iteration's match per query (may be null)
+    uint32_t* node_io;         // in: leaf that held last iteration's match; out: this iteration's (may be null)
+    const uint32_t* __restrict__ parent;
+    uint32_t* tile_node;       // tile kernel: per-tile start node of the last search (may be null)
+    StatA* part_a;
+    const LoopState* state;
+    unsigned long long* counters;  // [0] fast-path answers, [1] literal fallbacks, [2] tile lanes sent to the per-thread search,
+                                   // [3] candidates scanned by tiles (may be null)
+    int apply_pending;
+    int mode;                  // 0: literal traversal from the root; 1: per-thread fast path; 2: warp tiles
+    double init_best;
+    uint32_t pos_of_idx0;
+};
+
+struct NodeRegs {
+    double lo[3], hi[3];
+    uint32_t child0, pt0, npts, meta;
+};
+
+__device__ __forceinline__ NodeRegs load_node(const Node* __restrict__ nodes, uint32_t i) {
+    const int4* p = reinterpret_cast<const int4*>(nodes + i);
+    int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    NodeRegs r;
+    r.lo[0] = __hiloint2double(a.y, a.x);
+    r.lo[1] = __hiloint2double(a.w, a.z);
+    r.lo[2] = __hiloint2double(b.y, b.x);
+    r.hi[0] = __hiloint2double(b.w, b.z);
+    r.hi[1] = __hiloint2double(c.y, c.x);
+    r.hi[2] = __hiloint2double(c.w, c.z);
+    r.child0 = (uint32_t)d.x;
+    r.pt0 = (uint32_t)d.y;
+    r.npts = (uint32_t)d.z;
+    r.meta = (uint32_t)d.w;
+    return r;
+}
+
+__device__ __forceinline__ void load_point(const TPoint* __restrict__ pts, uint32_t i, double& x, double& y, double& z,
+                                           uint32_t& idx) {
+    const int4* p = reinterpret_cast<const int4*>(pts + i);
+    int4 a = __ldg(p), b = __ldg(p + 1);
+    x = __hiloint2double(a.y, a.x);
+    y = __hiloint2double(a.w, a.z);
+    z = __hiloint2double(b.y, b.x);
+    idx = (uint32_t)b.z;
+}
+
+// OctreeNode::minDistanceTo's per-axis term: max(0, max(lo - q, q - hi))   (octree.cpp:34-36)
+__device__ __forceinline__ double axis_dist(double lo, double hi, double q) {
+    return stdmax(0.0, stdmax(dsub(lo, q), dsub(q, hi)));
+}
+
+struct Search {
+    double best;       // best squared distance so far
+    uint32_t pos;      // its position in the sorted target, NONE while nothing accepted
+    uint32_t idx;      // its original index
+};
+
+// ---------------------------------------------------------------------------------------------------
+// The reference traversal from the root (whose own prune test the caller has already made).
+// stk: this thread's column of the shared stack (row stride STRIDE).
+// ---------------------------------------------------------------------------------------------------
+template <int STRIDE>
+__device__ __forceinline__ void dfs_literal(const Node* __restrict__ nodes, const TPoint* __restrict__ pts, const double qx,
+                                            const double qy, const double qz, Search& S, uint2* stk) {
+    int sp = 0;
+    uint32_t cur = 0;
+    bool have_cur = true;
+    for (;;) {
+        if (have_cur) {
+            const NodeRegs nd = load_node(nodes, cur);
+            const uint32_t mask = nd.meta & 0xFFu;
+            if (mask == 0) {
+                // leaf: octree.cpp:139-150.  The reference scans ascending original index with a strict <,
+                // i.e. within one leaf the smallest distance wins and equal distances go to the lowest index;
+                // points here are in key order, so that rule is applied explicitly.
+                bool from_this_leaf = false;
+                for (uint32_t k = 0; k < nd.npts; ++k) {
+                    double px, py, pz;
+                    uint32_t pidx;
+                    load_point(pts, nd.pt0 + k, px, py, pz, pidx);
+                    const double d2 = sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz));
+                    if (d2 < S.best || (from_this_leaf && d2 == S.best && pidx < S.idx)) {
+                        S.best = d2;
+                        S.pos = nd.pt0 + k;
+                        S.idx = pidx;
+                        from_this_leaf = true;
+                    }
+                }
+                have_cur = false;
+            } else {
+                // inner node: octree.cpp:152-171
+                double dl[3], dh[3];
+                const double q[3] = {qx, qy, qz};
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const double mid = dmul(dadd(nd.lo[a], nd.hi[a]), 0.5);
+                    const double l = axis_dist(nd.lo[a], mid, q[a]);
+                    const double h = axis_dist(mid, nd.hi[a], q[a]);
+                    dl[a] = dmul(l, l);
+                    dh[a] = dmul(h, h);
+                }
+                double md[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    const double s = dadd(dadd((o & 1) ? dh[0] : dl[0], (o & 2) ? dh[1] : dl[1]), (o & 4) ? dh[2] : dl[2]);
+                    md[o] = ((mask >> o) & 1u) ? dsqrt(s) : ICPB_INF;
+                }
+                // rank = position after a stable ascending sort by md (std::sort on <= 8 items == insertion sort)
+                uint32_t word = 0;
+                double mdmin = md[0];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t r = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < i) r += (md[j] <= md[i]) ? 1u : 0u;
+                        if (j > i) r += (md[j] < md[i]) ? 1u : 0u;
+                    }
+                    word |= (uint32_t)i << (3 * r);
+                    if (i > 0) mdmin = fmin(mdmin, md[i]);
+                }
+                const uint32_t cnt = __popc(mask);
+                const double m0 = dmul(mdmin, mdmin);
+                if (m0 >= S.best) {
+                    have_cur = false;  // nearest child pruned => all children pruned (octree.cpp:134-135)
+                } else {
+                    const uint32_t oct = word & 7u;
+                    if (cnt > 1) {
+                        // entry: x = node, y = order word (24 bits) | next position (4 bits) | count (4 bits)
+                        stk[sp * STRIDE] = make_uint2(cur, (word & 0xFFFFFFu) | (1u << 24) | (cnt << 28));
+                        ++sp;
+                    }
+                    cur = nd.child0 + __popc(mask & ((1u << oct) - 1u));
+                }
+            }
+        } else {
+            if (sp == 0) break;
+            uint2 top = stk[(sp - 1) * STRIDE];
+            const uint32_t k = (top.y >> 24) & 0xFu, cnt = top.y >> 28;
+            const uint32_t oct = (top.y >> (3 * k)) & 7u;
+            const NodeRegs pn = load_node(nodes, top.x);
+            const double q[3] = {qx, qy, qz};
+            double d[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double mid = dmul(dadd(pn.lo[a], pn.hi[a]), 0.5);
+                const bool up = (oct >> a) & 1u;
+                d[a] = axis_dist(up ? mid : pn.lo[a], up ? pn.hi[a] : mid, q[a]);
+            }
+            const double mdc = dsqrt(sumsq3(d[0], d[1], d[2]));
+            const double m = dmul(mdc, mdc);
+            if (m >= S.best) {
+                --sp;  // this sibling and every later one (larger distance) are pruned
+                continue;
+            }
+            if (k + 1 >= cnt) {
+                --sp;
+            } else {
+                top.y = (top.y & ~(0xFu << 24)) | ((k + 1) << 24);
+                stk[(sp - 1) * STRIDE] = top;
+            }
+            const uint32_t mask = pn.meta & 0xFFu;
+            cur = pn.child0 + __popc(mask & ((1u << oct) - 1u));
+            have_cur = true;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fast path: exact minimum of s and the runner-up, un-rooted bounds, any visiting order.
+// Stack entries: x = child0 of the parent, y = parent's child mask | (octants still to visit << 8).
+// ---------------------------------------------------------------------------------------------------
+struct Fast {
+    double best, second, bound;
+    uint32_t pos, node;
+};
+
+__device__ __forceinline__ void fast_take(Fast& F, double s, uint32_t pos, uint32_t node) {
+    const double grow = 1.0 + 1.8189894035458565e-12;  // 1 + 2^-39
+    if (s < F.best) {
+        F.second = F.best;
+        F.best = s;
+        F.pos = pos;
+        F.node = node;
+        const double b = dmul(s, grow);
+        F.bound = b < F.bound ? b : F.bound;
+    } else if (s < F.second) {
+        F.second = s;
+    }
+}
+
+template <int STRIDE>
+__device__ __forceinline__ void fast_search(const Node* __restrict__ nodes, const TPoint* __restrict__ pts, const double qx,
+                                            const double qy, const double qz, uint32_t start, Fast& F, uint2* stk) {
+    uint2* top = stk;  // one past the last entry of this thread's column
+    uint32_t cur = start;
+    for (;;) {
+        const NodeRegs nd = load_node(nodes, cur);
+        const uint32_t mask = nd.meta & 0xFFu;
+        bool descend = false;
+        if (mask == 0) {
+            const double sb = sumsq3(axis_dist(nd.lo[0], nd.hi[0], qx), axis_dist(nd.lo[1], nd.hi[1], qy),
+                                     axis_dist(nd.lo[2], nd.hi[2], qz));
+            if (sb <= F.bound) {
+                for (uint32_t k = 0; k < nd.npts; ++k) {
+                    double px, py, pz;
+                    uint32_t pidx;
+                    load_point(pts, nd.pt0 + k, px, py, pz, pidx);
+                    fast_take(F, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)), nd.pt0 + k, cur);
+                }
+            }
+        } else {
+            double dl[3], dh[3];
+            const double q[3] = {qx, qy, qz};
+            uint32_t oq = 0;  // octant of the query inside this node (visited first: it tightens the bound)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double mid = dmul(dadd(nd.lo[a], nd.hi[a]), 0.5);
+                const double l = axis_dist(nd.lo[a], mid, q[a]);
+                const double h = axis_dist(mid, nd.hi[a], q[a]);
+                dl[a] = dmul(l, l);
+                dh[a] = dmul(h, h);
+                oq |= (q[a] > mid ? 1u : 0u) << a;
+            }
+            uint32_t surv = 0;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                const double s = dadd(dadd((o & 1) ? dh[0] : dl[0], (o & 2) ? dh[1] : dl[1]), (o & 4) ? dh[2] : dl[2]);
+                surv |= (s <= F.bound ? 1u : 0u) << o;
+            }
+            surv &= mask;
+            if (surv) {
+                const uint32_t o = ((surv >> oq) & 1u) ? oq : (uint32_t)(__ffs(surv) - 1);
+                surv &= ~(1u << o);
+                if (surv) {
+                    *top = make_uint2(nd.child0, mask | (surv << 8));
+                    top += STRIDE;
+                }
+                cur = nd.child0 + __popc(mask & ((1u << o) - 1u));
+                descend = true;
+            }
+        }
+        if (descend) continue;
+        // next pending sibling
+        if (top == stk) break;
+        uint2 e = *(top - STRIDE);
+        uint32_t surv = e.y >> 8;
+        const uint32_t o = (uint32_t)(__ffs(surv) - 1);
+        surv &= surv - 1u;
+        if (surv) {
+            e.y = (e.y & 0xFFu) | (surv << 8);
+            *(top - STRIDE) = e;
+        } else {
+            top -= STRIDE;
+        }
+        cur = e.x + __popc((e.y & 0xFFu) & ((1u << o) - 1u));
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// One query, one thread: the fast path (temporal or point-location start) with the literal reference traversal
+// as fallback.  Returns the sorted target position of the answer (NONE if the reference accepts no point).
+//   pp / pn     last iteration's match and the leaf that held it (NONE if unknown)
+//   extra_seed  squared distance of some real target point already known (or +inf)
+// ---------------------------------------------------------------------------------------------------
+template <int STRIDE>
+__device__ __forceinline__ uint32_t per_thread_query(const NNArgs& A, const double qx, const double qy, const double qz,
+                                                     const bool finite_q, const uint32_t pp, const uint32_t pn,
+                                                     const double extra_seed, uint2* stk, uint32_t& result_node,
+                                                     bool& fell_back, const bool skip_fast = false) {
+    uint32_t result = NONE;
+    result_node = NONE;
+    bool need_literal = finite_q;
+    if (A.mode >= 1 && finite_q && !skip_fast) {
+        double Sd = ICPB_INF;
+        uint32_t start = 0;
+        if (pp != NONE && pn != NONE) {
+            // ---- temporal start: last iteration's match seeds the bound, its leaf seeds the start node ----
+            {
+                double px, py, pz;
+                uint32_t pidx;
+                load_point(A.pts, pp, px, py, pz, pidx);
+                Sd = sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz));
+            }
+            Sd = fmin(Sd, extra_seed);
+            const double clear_req = dmul(Sd, 1.0 + 3.637978807091713e-12);  // S (1 + 2^-38)
+            uint32_t n = pn;
+            NodeRegs nd;
+            bool inside_first = false, first = true;
+            for (;;) {  // climb until the query sits inside with enough clearance (the root always qualifies)
+                nd = load_node(A.nodes, n);
+                const double c = fmin(fmin(dsub(qx, nd.lo[0]), dsub(nd.hi[0], qx)),
+                                      fmin(fmin(dsub(qy, nd.lo[1]), dsub(nd.hi[1], qy)), fmin(dsub(qz, nd.lo[2]), dsub(nd.hi[2], qz))));
+                const double cf = (c > 0.0) ? (double)__double2float_rd(c) : 0.0;
+                if (first) inside_first = c >= 0.0;
+                first = false;
+                if (cf * cf > clear_req || n == 0u) break;
+                n = __ldg(A.parent + n);
+            }
+            if (!inside_first) {
+                // the query left last iteration's leaf: walk back down its own cell path while clearance allows
+                for (;;) {
+                    const uint32_t mask = nd.meta & 0xFFu;
+                    if (mask == 0) break;
+                    uint32_t oct = 0;
+                    oct |= (qx > dmul(dadd(nd.lo[0], nd.hi[0]), 0.5)) ? 1u : 0u;
+                    oct |= (qy > dmul(dadd(nd.lo[1], nd.hi[1]), 0.5)) ? 2u : 0u;
+                    oct |= (qz > dmul(dadd(nd.lo[2], nd.hi[2]), 0.5)) ? 4u : 0u;
+                    if (!((mask >> oct) & 1u)) break;
+                    const uint32_t ch = nd.child0 + __popc(mask & ((1u << oct) - 1u));
+                    const NodeRegs cd = load_node(A.nodes, ch);
+                    const double c = fmin(fmin(dsub(qx, cd.lo[0]), dsub(cd.hi[0], qx)),
+                                          fmin(fmin(dsub(qy, cd.lo[1]), dsub(cd.hi[1], qy)), fmin(dsub(qz, cd.lo[2]), dsub(cd.hi[2], qz))));
+                    const double cf = (c > 0.0) ? (double)__double2float_rd(c) : 0.0;
+                    if (!(cf * cf > clear_req)) break;
+                    n = ch;
+                    nd = cd;
+                }
+            }
+            start = n;
+        } else {
+            // ---- point location: walk down the cell path of q, remembering each level's clearance ----
+            uint32_t n = 0;
+            int level = 0;
+            NodeRegs nd;
+            // Running pointer rather than stk[level * STRIDE]: ptxas 12.9 (sm_100a) mis-addressed the indexed
+            // form of this store by two rows in the rotated loop (seen in SASS and on the device), PTX was correct.
+            uint2* path = stk;
+            for (;;) {
+                nd = load_node(A.nodes, n);
+                double c = fmin(fmin(dsub(qx, nd.lo[0]), dsub(nd.hi[0], qx)),
+                                fmin(fmin(dsub(qy, nd.lo[1]), dsub(nd.hi[1], qy)), fmin(dsub(qz, nd.lo[2]), dsub(nd.hi[2], qz))));
+                float cf = (c > 0.0) ? __double2float_rd(c) : 0.0f;
+                *path = make_uint2(n, __float_as_uint(cf));
+                const uint32_t mask = nd.meta & 0xFFu;
+                if (mask == 0) break;
+                uint32_t oct = 0;
+                oct |= (qx > dmul(dadd(nd.lo[0], nd.hi[0]), 0.5)) ? 1u : 0u;
+                oct |= (qy > dmul(dadd(nd.lo[1], nd.hi[1]), 0.5)) ? 2u : 0u;
+                oct |= (qz > dmul(dadd(nd.lo[2], nd.hi[2]), 0.5)) ? 4u : 0u;
+                if (!((mask >> oct) & 1u)) break;
+                n = nd.child0 + __popc(mask & ((1u << oct) - 1u));
+                ++level;
+                path += STRIDE;
+            }
+            // ---- seed: squared distance of a real target point of the located cell ----
+            const uint32_t ns = nd.npts < (uint32_t)SEED_SCAN ? nd.npts : (uint32_t)SEED_SCAN;
+            for (uint32_t k = 0; k < ns; ++k) {
+                double px, py, pz;
+                uint32_t pidx;
+                load_point(A.pts, nd.pt0 + k, px, py, pz, pidx);
+                Sd = fmin(Sd, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)));
+            }
+            if (pp != NONE) {
+                double px, py, pz;
+                uint32_t pidx;
+                load_point(A.pts, pp, px, py, pz, pidx);
+                Sd = fmin(Sd, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)));
+            }
+            Sd = fmin(Sd, extra_seed);
+            // ---- subtree start: deepest path node whose clearance^2 exceeds the seed bound ----
+            const double clear_req = dmul(Sd, 1.0 + 3.637978807091713e-12);  // S (1 + 2^-38)
+            for (int l = level; l > 0; --l) {
+                const uint2 e = *path;
+                path -= STRIDE;
+                const double cf = (double)__uint_as_float(e.y);
+                if (cf * cf > clear_req) {
+                    start = e.x;
+                    break;
+                }
+            }
+        }
+        if (Sd < 1e19) {  // also false for inf/NaN; keeps clear of the CLI's initial best 1e20
+            Fast F;
+            F.best = ICPB_INF;
+            F.second = ICPB_INF;
+            F.pos = NONE;
+            F.node = NONE;
+            F.bound = dmul(Sd, 1.0 + 1.8189894035458565e-12);                // S (1 + 2^-39)
+            fast_search<STRIDE>(A.nodes, A.pts, qx, qy, qz, start, F, stk);
+            // unique minimum with margin 2^-40 => order-independent => the reference's answer
+            if (F.pos != NONE && F.second > dmul(F.best, 1.0 + 9.094947017729282e-13)) {
+                result = F.pos;
+                result_node = F.node;
+                need_literal = false;
+            }
+        }
+    }
+    if (need_literal) {
+        // ---- the reference traversal from the root (octree.cpp:175-184) ----
+        Search S;
+        S.best = A.init_best;
+        S.pos = NONE;
+        S.idx = 0;
+        const NodeRegs root = load_node(A.rnodes, 0);
+        const double mdr = dsqrt(sumsq3(axis_dist(root.lo[0], root.hi[0], qx), axis_dist(root.lo[1], root.hi[1], qy),
+                                        axis_dist(root.lo[2], root.hi[2], qz)));
+        if (!(dmul(mdr, mdr) >= S.best)) dfs_literal<STRIDE>(A.rnodes, A.rpts, qx, qy, qz, S, stk);
+        result = (S.pos == NONE) ? NONE : __ldg(A.inv + S.idx);  // the reference's pick, as a search-tree position
+        fell_back = true;
+    }
+    return result;
+}
+
+// src = T * src (icpengine.cpp:345): ((T0 x + T1 y) + T2 z) + T3 * 1.0, no contraction
+__device__ __forceinline__ void apply_T_point(const double* T, double& qx, double& qy, double& qz) {
+    const double x = qx, y = qy, z = qz;
+    qx = dadd(dadd(dadd(dmul(T[0], x), dmul(T[1], y)), dmul(T[2], z)), T[3]);
+    qy = dadd(dadd(dadd(dmul(T[4], x), dmul(T[5], y)), dmul(T[6], z)), T[7]);
+    qz = dadd(dadd(dadd(dmul(T[8], x), dmul(T[9], y)), dmul(T[10], z)), T[11]);
+}
+
+}  // namespace icpb

@@ -153,6 +153,12 @@ class Handle:
         self.check(self.lib.icp_nn_counters(self.h, C.byref(a), C.byref(b), 1 if reset else 0))
         return a.value, b.value
 
+    def nn_tile_counters(self, reset=True):
+        """(tile lanes handed to the per-thread search, candidates scanned by tiles) since the last reset."""
+        a = C.c_int64(); b = C.c_int64()
+        self.check(self.lib.icp_nn_tile_counters(self.h, C.byref(a), C.byref(b), 1 if reset else 0))
+        return a.value, b.value
+
     # -- whole path ---------------------------------------------------------------------------------
     def _result(self, cap):
         hist = (_lib.IcpIteration * max(cap, 1))()

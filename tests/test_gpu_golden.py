@@ -1,0 +1,118 @@
+"""GPU tests against the committed golden vectors (tests/golden/, produced by the compiled reference -- see
+tools/make_golden.py): the CUDA path, through the C ABI, must reproduce the reference's own outputs.
+Bit-exact: octree structure and boxes, NN indices (engine and CLI variants, all three search modes), SVD given H,
+apply, inlier counts, iteration counts and exit paths.  1e-9 relative: RMSE and transforms of whole runs."""
+import os
+
+import numpy as np
+import pytest
+
+import clouds
+from golden_cases import CLI_RUNS, ENGINE_RUNS, TREE_CASES, kabsch_inputs, svd_inputs
+from iterativeclosestpoint_b200.engine import ICP, ICPParameters, VARIANT_CLI, VARIANT_ENGINE
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REL_E2E = 1e-9
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(1e-300, float(np.max(np.abs(b)))))
+
+
+@pytest.mark.parametrize("name,make,leaf,depth", TREE_CASES, ids=[c[0] for c in TREE_CASES])
+def test_octree_and_nn_match_reference_vectors(handle, name, make, leaf, depth):
+    g = load("tree_" + name)
+    tgt = make()
+    handle.octree_build(tgt, leaf, depth)
+    d = handle.octree_dump()
+    for k in ("depth", "key", "leaf", "count", "idx", "box"):
+        assert np.array_equal(d[k], g["tree_" + k]), f"{name}: tree field {k}"
+    qsets = {k: v[:1500] for k, v in clouds.query_sets(tgt).items()}
+    if name == "lattice_exact":
+        qsets["ties"] = clouds.lattice_tie_queries(tgt)
+    for variant, tag in ((VARIANT_ENGINE, "engine"), (VARIANT_CLI, "cli")):
+        handle.set_params(ICPParameters(octreeMaxPoints=leaf, octreeMaxDepth=depth), variant)
+        for mode in (0, 1, 2):
+            handle.set_option("nn_mode", mode)
+            for qname, q in qsets.items():
+                key = f"nn_{tag}_{qname}"
+                if key not in g.files:
+                    continue
+                idx, _, _ = handle.nn_query(q)
+                assert np.array_equal(idx, g[key]), f"{name}/{qname}/{tag}/mode{mode}"
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["thread", "tile"])
+@pytest.mark.parametrize("name,make,kw", ENGINE_RUNS, ids=[c[0] for c in ENGINE_RUNS])
+def test_engine_runs_match_reference_vectors(handle, name, make, kw, mode):
+    g = load("engine_" + name)
+    src, tgt = make()
+    kw = dict(kw)
+    stop_after = kw.pop("stop_after", -1)
+    p = ICPParameters(maxIterations=kw.get("max_iterations", 50), tolerance=kw.get("tolerance", 1e-6),
+                      sigmaMultiplier=kw.get("sigma", 3.0), octreeMaxPoints=kw.get("leaf", 10),
+                      octreeMaxDepth=kw.get("depth", 20))
+    handle.set_params(p, VARIANT_ENGINE)
+    handle.set_option("nn_mode", mode)
+    work = src.copy()
+    if stop_after >= 0:
+        import ctypes as C
+        flag = C.c_int(0)
+        seen = []
+        handle.set_callbacks(on_iteration=lambda r: (seen.append(r.iteration), setattr(flag, "value", 1 if len(seen) >= stop_after else 0)))
+        r = handle.register(work, tgt, stop_flag=flag)
+    else:
+        r = handle.register(work, tgt)
+    assert r.status == int(g["status"]) and r.success == bool(g["success"])
+    assert r.totalIterations == int(g["total_iterations"])
+    assert len(r.iterationHistory) == len(g["hist_rmse"])
+    for k, h in enumerate(r.iterationHistory):
+        assert h.iteration == g["hist_iteration"][k]
+        assert h.validPoints == g["hist_valid"][k] and h.outlierPoints == g["hist_outlier"][k]
+        assert h.hasAngles == bool(g["hist_has_angles"][k])
+        assert abs(h.rmse - g["hist_rmse"][k]) <= REL_E2E * max(g["hist_rmse"][k], 1e-300)
+        assert rel(h.transform, g["hist_T"][k]) <= REL_E2E
+    if r.success:
+        assert abs(r.finalRMSE - float(g["final_rmse"])) <= REL_E2E * float(g["final_rmse"])
+        assert rel(r.finalR, g["final_R"]) <= REL_E2E
+        assert np.max(np.abs(r.finalT - g["final_t"])) <= REL_E2E * max(1.0, float(np.max(np.abs(g["final_t"]))))
+        s = work[::37]
+        assert np.max(np.abs(s - g["source_out_sample"])) <= REL_E2E * float(np.max(np.abs(s)))
+    else:
+        assert np.array_equal(work, src)  # failure exits leave the source untouched
+
+
+@pytest.mark.parametrize("name,make,kw", CLI_RUNS, ids=[c[0] for c in CLI_RUNS])
+def test_cli_runs_match_reference_vectors(handle, name, make, kw):
+    g = load("cli_" + name)
+    src, tgt = make()
+    work = src.copy()
+    R, t, its = ICP(work, tgt, kw["max_iterations"], kw["tolerance"], handle=handle)
+    assert len(its) == len(g["iteration_T"])
+    for T, gT in zip(its, g["iteration_T"]):
+        assert rel(T, gT) <= REL_E2E
+    assert rel(R, g["final_R"]) <= 1e-8 and np.max(np.abs(t - g["final_t"])) <= 1e-8
+    s = work[::37]
+    assert np.max(np.abs(s - g["source_out_sample"])) <= REL_E2E * float(np.max(np.abs(s)))
+
+
+def test_svd_kabsch_apply_match_reference_vectors(handle):
+    g = load("kabsch_svd")
+    Hs, cAs, cBs = svd_inputs()
+    for i in range(len(Hs)):
+        T, U, S, V = handle.solve_from_H(Hs[i], cAs[i], cBs[i])
+        assert np.array_equal(U, g["U"][i]) and np.array_equal(S, g["S"][i]) and np.array_equal(V, g["V"][i]), i
+        assert np.array_equal(T, g["T"][i]), i
+    for i, (a, b) in enumerate(kabsch_inputs()):
+        Tm = g[f"kabsch{i}_T_engine"]
+        assert np.array_equal(handle.apply_transform(Tm, a)[::11], g[f"kabsch{i}_applied_sample"])
+        if i < 3:
+            T = handle.best_fit_transform(a, b)
+            assert rel(T[:3, :3], Tm[:3, :3]) <= 1e-10
+            assert np.max(np.abs(T[:3, 3] - Tm[:3, 3])) <= 1e-9 * max(1.0, float(np.max(np.abs(a))))

@@ -6,13 +6,13 @@ from iterativeclosestpoint_b200.engine import Handle, ICPParameters
 m=int(sys.argv[1]) if len(sys.argv)>1 else 10_000_000
 for regime in (sys.argv[2:] or ['primary','stress']):
     src,tgt=synth.make_pair(m,3,regime)
-    for mode in (1,0):
+    for mode in (2,1):
         h=Handle(0); h.set_option('nn_mode',mode)
-        h.set_params(ICPParameters(maxIterations=16 if mode==1 else 3))
+        h.set_params(ICPParameters(maxIterations=16))
         w=src.copy(); t0=time.time(); r=h.register(w,tgt); dt=time.time()-t0
         print(f'{regime} m={m} mode={mode} iters={r.loopIterations} wall={dt:.3f}s timings={ {k:round(v,2) for k,v in r.timings_ms.items()} }')
         print('   nn_ms:',[round(i.nnMs,2) for i in r.iterationHistory])
         print('   it_ms:',[round(i.iterMs,2) for i in r.iterationHistory])
-        print('   counters', h.nn_counters())
+        print('   counters', h.nn_counters(), 'tile (per-thread lanes, candidates)', h.nn_tile_counters())
         print('   rmse :',[round(i.rmse,4) for i in r.iterationHistory])
         h.close()
