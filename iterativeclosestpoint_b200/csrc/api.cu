@@ -441,7 +441,7 @@ int icp_create(icp_handle* out, int device_id) {
     if (cudaHostGetDevicePointer(&c->d_rec, c->h_rec, 0) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (getenv("ICP_B200_DEBUG_COUNTERS")) c->opt_count = true;
     const char* m = getenv("ICP_B200_NN_MODE");
-    if (m) c->opt_nn_mode = std::min(std::max(atoi(m), 0), 2);
+    if (m) c->opt_nn_mode = std::min(std::max(atoi(m), 0), 3);
     *out = (icp_handle)c;
     return ICP_OK;
 }
@@ -507,10 +507,13 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     Ctx* c = (Ctx*)h;
     if (!c || !key) return ICP_INVALID_ARGUMENT;
     if (!strcmp(key, "nn_mode")) {
-        c->opt_nn_mode = value < 0.5 ? 0 : (value < 1.5 ? 1 : 2);
+        c->opt_nn_mode = value < 0.5 ? 0 : (value < 1.5 ? 1 : (value < 2.5 ? 2 : 3));
         c->prev_valid = false;
     }
     else if (!strcmp(key, "count")) c->opt_count = value != 0.0;
+    else if (!strcmp(key, "grid_shift")) c->opt_grid_shift = (int)value;
+    else if (!strcmp(key, "walk_max_cells")) c->opt_walk_max_cells = std::max((int)value, 1);
+    else if (!strcmp(key, "terminal_pts")) c->opt_terminal_pts = std::min(std::max((int)value, 1), 1024);
     else if (!strcmp(key, "search_leaf")) c->opt_search_leaf = std::min(std::max((int)value, 1), 1024);
     else if (!strcmp(key, "order_queries")) c->opt_order_queries = value != 0.0;
     else if (!strcmp(key, "write_mask")) c->opt_write_mask = value != 0.0;

@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(128) node_emit_kernel(Node* __restrict__ nodes
                                                         const uint64_t* __restrict__ keys, int level, int max_pts,
                                                         int max_depth, const uint32_t* __restrict__ child_off,
                                                         uint32_t next_first, uint32_t* __restrict__ leaf_counter,
-                                                        uint32_t* __restrict__ parent) {
+                                                        uint32_t* __restrict__ parent, uint64_t* __restrict__ cell) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     Node nd = nodes[first + t];
@@ -432,6 +432,13 @@ __global__ void __launch_bounds__(128) node_emit_kernel(Node* __restrict__ nodes
             ch.meta = ((uint32_t)(level + 1) << 8);
             nodes[c0 + k] = ch;
             parent[c0 + k] = first + t;
+            if (cell) {  // integer cell coordinates of the child at its depth, 21 bits per axis
+                const uint64_t pc = cell[first + t];
+                const uint64_t cx = ((pc & 0x1FFFFFull) << 1) | (oct & 1u);
+                const uint64_t cy = (((pc >> 21) & 0x1FFFFFull) << 1) | ((oct >> 1) & 1u);
+                const uint64_t cz = (((pc >> 42) & 0x1FFFFFull) << 1) | ((oct >> 2) & 1u);
+                cell[c0 + k] = cx | (cy << 21) | (cz << 42);
+            }
             mask |= 1u << oct;
             ++k;
         }
@@ -465,6 +472,8 @@ static void tree_free(DeviceOctree& t) {
     if (t.parent) cudaFree(t.parent);
     if (t.pts) cudaFree(t.pts);
     if (t.inv_perm) cudaFree(t.inv_perm);
+    if (t.cell) cudaFree(t.cell);
+    if (t.grid) cudaFree(t.grid);
     t = DeviceOctree();
 }
 
@@ -478,17 +487,22 @@ static int grow_nodes(Ctx* c, DeviceOctree& t, int64_t need) {
     int64_t cap = std::max<int64_t>(need + need / 2, 1024);
     Node* nn = nullptr;
     uint32_t* np = nullptr;
+    uint64_t* nc = nullptr;
     ICPB_CUDA(c, cudaMalloc(&nn, (size_t)cap * sizeof(Node)));
     ICPB_CUDA(c, cudaMalloc(&np, (size_t)cap * sizeof(uint32_t)));
+    if (t.want_cell) ICPB_CUDA(c, cudaMalloc(&nc, (size_t)cap * sizeof(uint64_t)));
     if (t.nodes) {
         ICPB_CUDA(c, cudaMemcpyAsync(nn, t.nodes, (size_t)t.n_nodes * sizeof(Node), cudaMemcpyDeviceToDevice, c->stream));
         ICPB_CUDA(c, cudaMemcpyAsync(np, t.parent, (size_t)t.n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+        if (nc) ICPB_CUDA(c, cudaMemcpyAsync(nc, t.cell, (size_t)t.n_nodes * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
         ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
         ICPB_CUDA(c, cudaFree(t.nodes));
         ICPB_CUDA(c, cudaFree(t.parent));
+        if (t.cell) ICPB_CUDA(c, cudaFree(t.cell));
     }
     t.nodes = nn;
     t.parent = np;
+    t.cell = nc;
     t.cap_nodes = cap;
     return ICP_OK;
 }
@@ -499,6 +513,7 @@ static int grow_nodes(Ctx* c, DeviceOctree& t, int64_t need) {
 // to match anything in the reference.
 static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, int max_pts, int max_depth, bool cubic) {
     tree_free(t);
+    t.want_cell = cubic;
     t.max_pts = max_pts;
     t.max_depth = max_depth;
     t.n_pts = m;
@@ -545,6 +560,7 @@ static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, i
     // K3
     ICPB_TRY(grow_nodes(c, t, std::max<int64_t>(m / 2, 1024)));
     ICPB_CUDA(c, cudaMemsetAsync(t.parent, 0xFF, sizeof(uint32_t), s));
+    if (t.cell) ICPB_CUDA(c, cudaMemsetAsync(t.cell, 0, sizeof(uint64_t), s));
     root_node_kernel<<<1, 32, 0, s>>>(t.nodes, d_root, (uint32_t)m);
     c->launches++;
     t.n_nodes = 1;
@@ -563,7 +579,7 @@ static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, i
         const uint32_t next_first = first + count;
         ICPB_TRY(grow_nodes(c, t, (int64_t)next_first + n_children));
         node_emit_kernel<<<nb, 128, 0, s>>>(t.nodes, first, count, keys, level, max_pts, max_depth, offs, next_first,
-                                            d_misc + 1, t.parent);
+                                            d_misc + 1, t.parent, t.cell);
         c->launches++;
         t.n_nodes = (int64_t)next_first + n_children;
         if (n_children == 0) break;
@@ -596,6 +612,88 @@ static int build_inv_perm_of(Ctx* c, DeviceOctree& t) {
     return ICP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Entry grid of the search tree: a dense array over the cloud's bounding box whose cells are the search tree's
+// cells at one level L; each entry holds the node that owns the cell (the depth-L node, or the shallower leaf
+// covering it), NONE where there is no point.  Lets a query jump to the few cells its search ball touches
+// instead of walking down from the root or up from a previous leaf.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) leaf_depth_hist_kernel(const Node* __restrict__ nodes, int64_t n_nodes,
+                                                              unsigned long long* __restrict__ hist /* [32] */) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const uint32_t meta = nodes[i].meta;
+    if ((meta & 0xFFu) == 0u) atomicAdd(&hist[(meta >> 8) & 0x1Fu], (unsigned long long)nodes[i].npts);
+}
+
+__global__ void __launch_bounds__(128) grid_fill_kernel(const Node* __restrict__ nodes, const uint64_t* __restrict__ cell,
+                                                        int64_t n_nodes, int level, int nx, int ny, int nz,
+                                                        uint32_t* __restrict__ grid) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const uint32_t meta = nodes[i].meta;
+    const int d = (int)((meta >> 8) & 0xFFu);
+    const bool leaf = (meta & 0xFFu) == 0u;
+    if (!(d == level || (leaf && d < level))) return;
+    const uint64_t pc = cell[i];
+    const int sh = level - d;
+    const long long x0 = (long long)(pc & 0x1FFFFFull) << sh, y0 = (long long)((pc >> 21) & 0x1FFFFFull) << sh,
+                    z0 = (long long)((pc >> 42) & 0x1FFFFFull) << sh;
+    const long long bs = 1ll << sh;
+    const long long x1 = min(x0 + bs, (long long)nx), y1 = min(y0 + bs, (long long)ny), z1 = min(z0 + bs, (long long)nz);
+    for (long long z = z0; z < z1; ++z)
+        for (long long y = y0; y < y1; ++y)
+            for (long long x = x0; x < x1; ++x) grid[(z * ny + y) * nx + x] = (uint32_t)i;
+}
+
+static int build_grid(Ctx* c, DeviceOctree& t) {
+    cudaStream_t s = c->stream;
+    ICPB_TRY(devbuf_reserve(c, c->scratch0, 64 * sizeof(unsigned long long)));
+    unsigned long long* d_hist = (unsigned long long*)c->scratch0.p;
+    ICPB_CUDA(c, cudaMemsetAsync(d_hist, 0, 32 * sizeof(unsigned long long), s));
+    leaf_depth_hist_kernel<<<(int)((t.n_nodes + 255) / 256), 256, 0, s>>>(t.nodes, t.n_nodes, d_hist);
+    c->launches++;
+    unsigned long long hist[32];
+    ICPB_CUDA(c, cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, s));
+    ICPB_CUDA(c, cudaStreamSynchronize(s));
+    // level = the depth that holds the median point's leaf (cells there carry about one leaf of points) ...
+    unsigned long long acc = 0;
+    int level = 0;
+    for (int d = 0; d < 32; ++d) {
+        acc += hist[d];
+        if (2 * acc >= (unsigned long long)t.n_pts) {
+            level = d;
+            break;
+        }
+    }
+    level = std::min(level + c->opt_grid_shift, 21);
+    level = std::max(level, 0);
+    // ... lowered until the dense array over the bounding box stays within the cell budget
+    const double cube = t.root_hi[0] - t.root_lo[0];
+    double ext[3];
+    for (int a = 0; a < 3; ++a) ext[a] = c->tree.root_hi[a] - t.root_lo[a];  // the cloud's own extent (reference root box)
+    long long nx, ny, nz;
+    for (;; --level) {
+        const double g = cube / (double)(1ll << level);
+        nx = (long long)(ext[0] / g) + 1;
+        ny = (long long)(ext[1] / g) + 1;
+        nz = (long long)(ext[2] / g) + 1;
+        if ((double)nx * (double)ny * (double)nz <= (double)c->opt_grid_max_cells || level == 0) break;
+    }
+    t.grid_level = level;
+    t.gnx = (int)nx;
+    t.gny = (int)ny;
+    t.gnz = (int)nz;
+    t.grid_cell = cube / (double)(1ll << level);
+    const size_t cells = (size_t)(nx * ny * nz);
+    ICPB_CUDA(c, cudaMalloc(&t.grid, cells * sizeof(uint32_t)));
+    ICPB_CUDA(c, cudaMemsetAsync(t.grid, 0xFF, cells * sizeof(uint32_t), s));
+    grid_fill_kernel<<<(int)((t.n_nodes + 127) / 128), 128, 0, s>>>(t.nodes, t.cell, t.n_nodes, level, t.gnx, t.gny, t.gnz, t.grid);
+    c->launches++;
+    ICPB_CUDA(c, cudaGetLastError());
+    return ICP_OK;
+}
+
 // The reference's tree (c->tree: structure parity, literal traversal) and the isotropic search tree (c->fast: every
 // fast search path, and the canonical point order that match positions refer to).
 int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int max_depth) {
@@ -609,6 +707,7 @@ int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int
     ICPB_TRY(build_tree(c, c->tree, d_xyz, m, max_pts, max_depth, false));
     ICPB_TRY(build_tree(c, c->fast, d_xyz, m, c->opt_search_leaf, 21, true));
     ICPB_TRY(build_inv_perm_of(c, c->fast));  // original index -> search-tree position (literal results, stage API)
+    ICPB_TRY(build_grid(c, c->fast));
     return ICP_OK;
 }
 

@@ -21,6 +21,12 @@ struct DeviceOctree {
     double root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};
     uint32_t pos_of_idx0 = 0;  // sorted position of original point 0 (findNearest's default answer)
     uint32_t* inv_perm = nullptr;  // original index -> sorted position (built lazily for the stage API)
+    // search tree only: integer cell coordinates per node and the dense entry grid at level grid_level
+    bool want_cell = false;
+    uint64_t* cell = nullptr;
+    uint32_t* grid = nullptr;
+    int grid_level = 0, gnx = 0, gny = 0, gnz = 0;
+    double grid_cell = 0.0;
     bool valid = false;
 };
 
@@ -48,6 +54,10 @@ struct Ctx {
     DeviceOctree tree;  // the reference's octree (structure parity, literal traversal)
     DeviceOctree fast;  // isotropic search tree over the same points; match positions index ITS point order
     int opt_search_leaf = 16;        // leaf capacity of the search tree
+    int opt_terminal_pts = 16;       // tile kernel stages subtrees up to this size whole
+    int opt_grid_shift = 0;          // entry grid level relative to the median leaf depth
+    long long opt_grid_max_cells = 1ll << 26;
+    int opt_walk_max_cells = 27;     // cell walk gives way to the climbing search beyond this many cells
     DevBuf tgt_raw;  // original-order target AoS (kept for the stage API)
     int64_t n_tgt = 0;
 
@@ -62,7 +72,7 @@ struct Ctx {
     bool prev_valid = false;         // pos / node_io hold last run's matches of the resident source against the current tree
     float last_build_ms = 0.f;
     // tuning knobs (icp_set_option)
-    int opt_nn_mode = 2;             // 0: literal traversal from the root; 1: per-thread fast path; 2: warp tiles
+    int opt_nn_mode = 3;             // 0: literal traversal from the root; 1: per-thread fast path; 2: warp tiles
     bool opt_order_queries = true;   // Morton-order the source for traversal coherence
     bool opt_write_mask = false;     // keep the per-point inlier mask of the last iteration
     bool opt_count = false;          // maintain the NN path counters (same-address atomics: profiling / tests only)

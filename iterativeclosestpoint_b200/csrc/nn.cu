@@ -67,6 +67,8 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
         if (A.mode == 1 && A.prev_pos && A.node_io) {
             pp = A.prev_pos[i];
             pn = A.node_io[i];
+        } else if (A.mode == 3 && A.prev_pos) {
+            pp = A.prev_pos[i];
         }
         uint32_t result_node = NONE;
         const uint32_t result = per_thread_query<NN_THREADS>(A, qx, qy, qz, finite_q, pp, pn, ICPB_INF, stk, result_node, fell_back);
@@ -122,6 +124,15 @@ int nn_launch(Ctx* c, const NNLaunch& L) {
     A.rnodes = c->tree.nodes;
     A.rpts = c->tree.pts;
     A.inv = c->fast.inv_perm;
+    A.grid = c->fast.grid;
+    A.gnx = c->fast.gnx;
+    A.gny = c->fast.gny;
+    A.gnz = c->fast.gnz;
+    A.glevel = c->fast.grid_level;
+    A.gmax_cells = c->opt_walk_max_cells;
+    for (int a = 0; a < 3; ++a) A.gorg[a] = c->fast.root_lo[a];
+    A.ginv = 1.0 / c->fast.grid_cell;
+    A.geps = c->fast.grid_cell * 9.5367431640625e-07;  // cell * 2^-20 >> any rounding of the bisection boundaries
     A.sx = L.sx; A.sy = L.sy; A.sz = L.sz;
     A.ox = L.ox; A.oy = L.oy; A.oz = L.oz;
     A.n = L.n;
@@ -138,6 +149,7 @@ int nn_launch(Ctx* c, const NNLaunch& L) {
     A.init_best = L.init_best;
     A.pos_of_idx0 = c->fast.pos_of_idx0;
     A.tile_node = L.tile_node;
+    A.terminal_pts = c->opt_terminal_pts;
     if (L.mode == 2) return nn_tile_launch(c, A);
     nn_kernel<<<nn_grid_blocks(L.n), NN_THREADS, 0, c->stream>>>(A);
     c->launches++;

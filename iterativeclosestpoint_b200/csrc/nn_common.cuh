@@ -16,6 +16,10 @@ struct NNArgs {
     const Node* __restrict__ rnodes;   // the reference's octree and its point order: literal traversal only
     const TPoint* __restrict__ rpts;
     const uint32_t* __restrict__ inv;  // original target index -> position in `pts`
+    // entry grid of the search tree (build.cu): cell -> owning node, NONE where empty
+    const uint32_t* __restrict__ grid;
+    int gnx, gny, gnz, glevel, gmax_cells;
+    double gorg[3], ginv, geps;
     const double* sx;
     const double* sy;
     const double* sz;
@@ -34,7 +38,9 @@ struct NNArgs {
     unsigned long long* counters;  // [0] fast-path answers, [1] literal fallbacks, [2] tile lanes sent to the per-thread search,
                                    // [3] candidates scanned by tiles (may be null)
     int apply_pending;
-    int mode;                  // 0: literal traversal from the root; 1: per-thread fast path; 2: warp tiles
+    int terminal_pts;          // tile kernel: subtrees with at most this many points are staged whole
+    int mode;                  // 0: literal traversal from the root; 1: per-thread, climb from the last leaf; 2: warp tiles;
+                               // 3: per-thread, entry through the grid cells the search ball touches
     double init_best;
     uint32_t pos_of_idx0;
 };
@@ -286,6 +292,81 @@ __device__ __forceinline__ void fast_search(const Node* __restrict__ nodes, cons
 
 
 // ---------------------------------------------------------------------------------------------------
+// Cell walk (mode 3): the search ball around q (radius = distance to a known target point) touches a handful of
+// entry-grid cells; the exact minimum over the subtrees that own those cells is the exact minimum over the cloud,
+// because every point of any other cell differs from q by more than the radius along some axis.
+// Returns false if the walk does not apply (no seed, or too many cells) -- the caller then uses the climbing search.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int grid_cell_index(const NNArgs& A, double v, int a, int n) {
+    double f = floor(dmul(dsub(v, A.gorg[a]), A.ginv));
+    f = fmin(fmax(f, -1.0), (double)n);
+    return (int)f;
+}
+
+template <int STRIDE>
+__device__ __forceinline__ bool cell_walk(const NNArgs& A, const double qx, const double qy, const double qz, double Sd,
+                                          uint2* stk, Fast& F) {
+    if (!(Sd < 1e19)) {
+        // no seed yet: locate q's own cell, follow q's path below it and take the points found there
+        const int ix = grid_cell_index(A, qx, 0, A.gnx), iy = grid_cell_index(A, qy, 1, A.gny), iz = grid_cell_index(A, qz, 2, A.gnz);
+        if (ix < 0 || iy < 0 || iz < 0 || ix >= A.gnx || iy >= A.gny || iz >= A.gnz) return false;
+        uint32_t n = __ldg(A.grid + ((long long)iz * A.gny + iy) * A.gnx + ix);
+        if (n == NONE) return false;
+        NodeRegs nd = load_node(A.nodes, n);
+        for (;;) {
+            const uint32_t mask = nd.meta & 0xFFu;
+            if (mask == 0u) break;
+            uint32_t oct = 0;
+            oct |= (qx > dmul(dadd(nd.lo[0], nd.hi[0]), 0.5)) ? 1u : 0u;
+            oct |= (qy > dmul(dadd(nd.lo[1], nd.hi[1]), 0.5)) ? 2u : 0u;
+            oct |= (qz > dmul(dadd(nd.lo[2], nd.hi[2]), 0.5)) ? 4u : 0u;
+            if (!((mask >> oct) & 1u)) break;
+            n = nd.child0 + __popc(mask & ((1u << oct) - 1u));
+            nd = load_node(A.nodes, n);
+        }
+        const uint32_t ns = nd.npts < (uint32_t)SEED_SCAN ? nd.npts : (uint32_t)SEED_SCAN;
+        for (uint32_t k = 0; k < ns; ++k) {
+            double px, py, pz;
+            uint32_t pidx;
+            load_point(A.pts, nd.pt0 + k, px, py, pz, pidx);
+            Sd = fmin(Sd, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)));
+        }
+        if (!(Sd < 1e19)) return false;
+    }
+    const double r = dmul(dsqrt(Sd), 1.0 + 9.5367431640625e-07);  // sqrt(S) (1 + 2^-20)
+    const double e = dadd(r, A.geps);
+    int x0 = grid_cell_index(A, dsub(qx, e), 0, A.gnx), x1 = grid_cell_index(A, dadd(qx, e), 0, A.gnx);
+    int y0 = grid_cell_index(A, dsub(qy, e), 1, A.gny), y1 = grid_cell_index(A, dadd(qy, e), 1, A.gny);
+    int z0 = grid_cell_index(A, dsub(qz, e), 2, A.gnz), z1 = grid_cell_index(A, dadd(qz, e), 2, A.gnz);
+    x0 = max(x0, 0); y0 = max(y0, 0); z0 = max(z0, 0);
+    x1 = min(x1, A.gnx - 1); y1 = min(y1, A.gny - 1); z1 = min(z1, A.gnz - 1);
+    if ((long long)(x1 - x0 + 1) * (long long)(y1 - y0 + 1) * (long long)(z1 - z0 + 1) > (long long)A.gmax_cells) return false;
+    F.best = ICPB_INF;
+    F.second = ICPB_INF;
+    F.pos = NONE;
+    F.node = NONE;
+    F.bound = dmul(Sd, 1.0 + 1.8189894035458565e-12);  // S (1 + 2^-39)
+    for (int z = z0; z <= z1; ++z)
+        for (int y = y0; y <= y1; ++y)
+            for (int x = x0; x <= x1; ++x) {
+                const uint32_t n = __ldg(A.grid + ((long long)z * A.gny + y) * A.gnx + x);
+                if (n == NONE) continue;
+                // a leaf shallower than the grid level owns a block of cells: search it once, from the first
+                // cell that the block and this query's range have in common
+                const NodeRegs nd = load_node(A.nodes, n);
+                const int d = (int)((nd.meta >> 8) & 0xFFu);
+                if (d < A.glevel) {
+                    const int bx = (int)floor(dmul(dsub(nd.lo[0], A.gorg[0]), A.ginv) + 0.5);
+                    const int by = (int)floor(dmul(dsub(nd.lo[1], A.gorg[1]), A.ginv) + 0.5);
+                    const int bz = (int)floor(dmul(dsub(nd.lo[2], A.gorg[2]), A.ginv) + 0.5);
+                    if (x != max(bx, x0) || y != max(by, y0) || z != max(bz, z0)) continue;
+                }
+                fast_search<STRIDE>(A.nodes, A.pts, qx, qy, qz, n, F, stk);
+            }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // One query, one thread: the fast path (temporal or point-location start) with the literal reference traversal
 // as fallback.  Returns the sorted target position of the answer (NONE if the reference accepts no point).
 //   pp / pn     last iteration's match and the leaf that held it (NONE if unknown)
@@ -299,7 +380,24 @@ __device__ __forceinline__ uint32_t per_thread_query(const NNArgs& A, const doub
     uint32_t result = NONE;
     result_node = NONE;
     bool need_literal = finite_q;
-    if (A.mode >= 1 && finite_q && !skip_fast) {
+    bool walked = false;
+    if (A.mode == 3 && finite_q && !skip_fast) {
+        double Sd = extra_seed;
+        if (pp != NONE) {
+            double px, py, pz;
+            uint32_t pidx;
+            load_point(A.pts, pp, px, py, pz, pidx);
+            Sd = fmin(Sd, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)));
+        }
+        Fast F;
+        walked = cell_walk<STRIDE>(A, qx, qy, qz, Sd, stk, F);
+        if (walked && F.pos != NONE && F.second > dmul(F.best, 1.0 + 9.094947017729282e-13)) {
+            result = F.pos;
+            result_node = F.node;
+            need_literal = false;
+        }
+    }
+    if (A.mode >= 1 && finite_q && !skip_fast && !walked) {
         double Sd = ICPB_INF;
         uint32_t start = 0;
         if (pp != NONE && pn != NONE) {

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 6) nn_tile_kernel(const NNArgs A
             }
             for (;;) {
                 const uint32_t mask = nd.meta & 0xFFu;
-                if (mask == 0u || nd.npts <= (uint32_t)TERMINAL_PTS) break;
+                if (mask == 0u || nd.npts <= (uint32_t)A.terminal_pts) break;
                 const uint32_t ov = overlap_octants(nd, elo, ehi);
                 if (__popc(ov) != 1) break;
                 const uint32_t o = (uint32_t)(__ffs(ov) - 1);
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 6) nn_tile_kernel(const NNArgs A
                     if (node != NONE) {
                         const NodeRegs nd = load_node(A.nodes, node);
                         mask = nd.meta & 0xFFu;
-                        if (mask == 0u || nd.npts <= (uint32_t)TERMINAL_PTS || box_inside(nd, elo, ehi)) {
+                        if (mask == 0u || nd.npts <= (uint32_t)A.terminal_pts || box_inside(nd, elo, ehi)) {
                             pend_pt0 = nd.pt0;
                             pend_n = (int)nd.npts;
                         } else {

@@ -58,7 +58,7 @@ def test_octree_structure_bit_exact(handle, oracle, name, make, leaf, depth):
     assert info.depth == int(want["depth"].max())
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2], ids=["literal", "thread", "tile"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3], ids=["literal", "climb", "tile", "walk"])
 @pytest.mark.parametrize("name,make,leaf,depth", TREE_CASES, ids=[c[0] for c in TREE_CASES])
 def test_nn_indices_bit_exact(handle, oracle, name, make, leaf, depth, mode):
     tgt = make()
@@ -76,7 +76,7 @@ def test_nn_indices_bit_exact(handle, oracle, name, make, leaf, depth, mode):
         assert np.array_equal(dist, d), f"{name}/{qname}: distances are not bit-identical"
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2], ids=["literal", "thread", "tile"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3], ids=["literal", "climb", "tile", "walk"])
 def test_nn_lattice_ties_follow_reference_traversal_order(handle, oracle, mode):
     """Exactly equidistant candidates: the winner is the first one the reference's DFS visits, not the lowest index."""
     lat = clouds.lattice_exact()
@@ -97,7 +97,7 @@ def test_nn_nonfinite_queries_return_index_zero(handle, oracle):
     q = np.array([[np.nan, 1.0, 1.0], [np.inf, 0.0, 0.0], [1.0, -np.inf, 2.0], [1e300, 1e300, 1e300], [5.0, 5.0, 1.0]])
     handle.octree_build(tgt)
     want = oracle.octree(tgt).find_nearest(q)
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         handle.set_option("nn_mode", mode)
         idx, _, _ = handle.nn_query(q)
         assert np.array_equal(idx, want)
@@ -110,7 +110,7 @@ def test_nn_cli_variant_initial_best(handle, oracle):
     handle.set_params(ICPParameters(), VARIANT_CLI)
     handle.octree_build(tgt)
     want = oracle.octree(tgt).find_nearest(q, variant=1)
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         handle.set_option("nn_mode", mode)
         idx, _, _ = handle.nn_query(q)
         assert np.array_equal(idx, want)
@@ -232,7 +232,7 @@ def _check_run(got, want, n_src, tol=REL_E2E):
         assert np.max(np.abs(got.finalT - want.final_t)) <= tol * max(1.0, float(np.max(np.abs(want.final_t))))
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2], ids=["literal", "thread", "tile"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3], ids=["literal", "climb", "tile", "walk"])
 def test_register_config1_engine(handle, oracle, mode):
     """BASELINE.json config #1: 10k-point cloud vs transformed + noised copy, 50 / 1e-6 / 3 sigma / 10 / 20."""
     src, tgt = synth.make_test_icp_pair(10000)
@@ -340,7 +340,7 @@ def test_full_size_config2_properties(handle, oracle):
     assert np.all(sdist == 0.0)
     assert np.array_equal(tgt[sidx], tgt[:200000])
     # all three search modes agree on every query
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         handle.set_option("nn_mode", mode)
         idx0, dist0, _ = handle.nn_query(src)
         assert np.array_equal(idx0, idx) and np.array_equal(dist0, dist)

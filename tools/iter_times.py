@@ -6,7 +6,7 @@ from iterativeclosestpoint_b200.engine import Handle, ICPParameters
 m=int(sys.argv[1]) if len(sys.argv)>1 else 10_000_000
 for regime in (sys.argv[2:] or ['primary','stress']):
     src,tgt=synth.make_pair(m,3,regime)
-    for mode in (2,1):
+    for mode in (3,2):
         h=Handle(0); h.set_option('nn_mode',mode)
         h.set_params(ICPParameters(maxIterations=16))
         w=src.copy(); t0=time.time(); r=h.register(w,tgt); dt=time.time()-t0

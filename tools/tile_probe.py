@@ -7,7 +7,9 @@ from iterativeclosestpoint_b200.engine import Handle, ICPParameters
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 regime = sys.argv[2] if len(sys.argv) > 2 else 'primary'
 src, tgt = synth.make_pair(m, 3, regime)
-h = Handle(0); h.set_option('nn_mode', 2)
+h = Handle(0); h.set_option('nn_mode', int(os.environ.get('ICP_MODE', '3')))
+for kv in os.environ.get('ICP_OPTS','').split(','):
+    if kv: h.set_option(kv.split('=')[0], float(kv.split('=')[1]))
 def cb(it):
     print(f"iter {it.iteration} nn_ms {it.nnMs:.2f} rmse {it.rmse:.4f}", flush=True)
     h.nn_tile_counters()
