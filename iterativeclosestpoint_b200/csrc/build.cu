@@ -628,13 +628,21 @@ __global__ void __launch_bounds__(256) leaf_depth_hist_kernel(const Node* __rest
 
 __global__ void __launch_bounds__(128) grid_fill_kernel(const Node* __restrict__ nodes, const uint64_t* __restrict__ cell,
                                                         int64_t n_nodes, int level, int nx, int ny, int nz,
-                                                        uint32_t* __restrict__ grid) {
+                                                        uint2* __restrict__ grid) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
-    const uint32_t meta = nodes[i].meta;
-    const int d = (int)((meta >> 8) & 0xFFu);
-    const bool leaf = (meta & 0xFFu) == 0u;
+    const Node nd = nodes[i];
+    const int d = (int)((nd.meta >> 8) & 0xFFu);
+    const bool leaf = (nd.meta & 0xFFu) == 0u;
     if (!(d == level || (leaf && d < level))) return;
+    // entry kinds, see nn_common.cuh (cell walk); a leaf with 2^24 points or more is entered through its node
+    uint2 e;
+    if (leaf && nd.npts < (1u << 24))
+        e = make_uint2(nd.pt0, nd.npts | ((uint32_t)d << 24) | ((d == level ? 1u : 2u) << 30));
+    else if (d == level)
+        e = make_uint2((uint32_t)i, 3u << 30);
+    else
+        return;  // (cannot happen: a shallower leaf that large has max_depth < level)
     const uint64_t pc = cell[i];
     const int sh = level - d;
     const long long x0 = (long long)(pc & 0x1FFFFFull) << sh, y0 = (long long)((pc >> 21) & 0x1FFFFFull) << sh,
@@ -643,7 +651,7 @@ __global__ void __launch_bounds__(128) grid_fill_kernel(const Node* __restrict__
     const long long x1 = min(x0 + bs, (long long)nx), y1 = min(y0 + bs, (long long)ny), z1 = min(z0 + bs, (long long)nz);
     for (long long z = z0; z < z1; ++z)
         for (long long y = y0; y < y1; ++y)
-            for (long long x = x0; x < x1; ++x) grid[(z * ny + y) * nx + x] = (uint32_t)i;
+            for (long long x = x0; x < x1; ++x) grid[(z * ny + y) * nx + x] = e;
 }
 
 static int build_grid(Ctx* c, DeviceOctree& t) {
@@ -686,8 +694,8 @@ static int build_grid(Ctx* c, DeviceOctree& t) {
     t.gnz = (int)nz;
     t.grid_cell = cube / (double)(1ll << level);
     const size_t cells = (size_t)(nx * ny * nz);
-    ICPB_CUDA(c, cudaMalloc(&t.grid, cells * sizeof(uint32_t)));
-    ICPB_CUDA(c, cudaMemsetAsync(t.grid, 0xFF, cells * sizeof(uint32_t), s));
+    ICPB_CUDA(c, cudaMalloc(&t.grid, cells * sizeof(uint2)));
+    ICPB_CUDA(c, cudaMemsetAsync(t.grid, 0, cells * sizeof(uint2), s));
     grid_fill_kernel<<<(int)((t.n_nodes + 127) / 128), 128, 0, s>>>(t.nodes, t.cell, t.n_nodes, level, t.gnx, t.gny, t.gnz, t.grid);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());

@@ -24,7 +24,7 @@ struct DeviceOctree {
     // search tree only: integer cell coordinates per node and the dense entry grid at level grid_level
     bool want_cell = false;
     uint64_t* cell = nullptr;
-    uint32_t* grid = nullptr;
+    uint2* grid = nullptr;
     int grid_level = 0, gnx = 0, gny = 0, gnz = 0;
     double grid_cell = 0.0;
     bool valid = false;

@@ -17,7 +17,7 @@ struct NNArgs {
     const TPoint* __restrict__ rpts;
     const uint32_t* __restrict__ inv;  // original target index -> position in `pts`
     // entry grid of the search tree (build.cu): cell -> owning node, NONE where empty
-    const uint32_t* __restrict__ grid;
+    const uint2* __restrict__ grid;
     int gnx, gny, gnz, glevel, gmax_cells;
     double gorg[3], ginv, geps;
     const double* sx;
@@ -222,6 +222,27 @@ __device__ __forceinline__ void fast_take(Fast& F, double s, uint32_t pos, uint3
     }
 }
 
+// Scans the points [pt0, pt0 + npts) of one leaf, four loads in flight at a time.  Points whose s exceeds the running
+// bound (<= min(seed, best) (1 + 2^-39)) can be neither the minimum nor a near-tie of it and are skipped.
+__device__ __forceinline__ void scan_leaf_points(const TPoint* __restrict__ pts, const uint32_t pt0, const uint32_t npts,
+                                                 const double qx, const double qy, const double qz, Fast& F,
+                                                 const uint32_t tag) {
+    for (uint32_t k = 0; k < npts; k += 4) {
+        double px[4], py[4], pz[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t kk = (k + j < npts) ? k + j : npts - 1u;
+            uint32_t pidx;
+            load_point(pts, pt0 + kk, px[j], py[j], pz[j], pidx);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double s = sumsq3(dsub(px[j], qx), dsub(py[j], qy), dsub(pz[j], qz));
+            if (k + j < npts && s <= F.bound) fast_take(F, s, pt0 + k + j, tag);
+        }
+    }
+}
+
 template <int STRIDE>
 __device__ __forceinline__ void fast_search(const Node* __restrict__ nodes, const TPoint* __restrict__ pts, const double qx,
                                             const double qy, const double qz, uint32_t start, Fast& F, uint2* stk) {
@@ -234,14 +255,7 @@ __device__ __forceinline__ void fast_search(const Node* __restrict__ nodes, cons
         if (mask == 0) {
             const double sb = sumsq3(axis_dist(nd.lo[0], nd.hi[0], qx), axis_dist(nd.lo[1], nd.hi[1], qy),
                                      axis_dist(nd.lo[2], nd.hi[2], qz));
-            if (sb <= F.bound) {
-                for (uint32_t k = 0; k < nd.npts; ++k) {
-                    double px, py, pz;
-                    uint32_t pidx;
-                    load_point(pts, nd.pt0 + k, px, py, pz, pidx);
-                    fast_take(F, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)), nd.pt0 + k, cur);
-                }
-            }
+            if (sb <= F.bound) scan_leaf_points(pts, nd.pt0, nd.npts, qx, qy, qz, F, cur);
         } else {
             double dl[3], dh[3];
             const double q[3] = {qx, qy, qz};
@@ -295,12 +309,18 @@ __device__ __forceinline__ void fast_search(const Node* __restrict__ nodes, cons
 // Cell walk (mode 3): the search ball around q (radius = distance to a known target point) touches a handful of
 // entry-grid cells; the exact minimum over the subtrees that own those cells is the exact minimum over the cloud,
 // because every point of any other cell differs from q by more than the radius along some axis.
+// Grid entries (uint2, build.cu): y >> 30 = kind: 0 empty; 1 leaf at the grid level (x = first point, y & 0xFFFFFF =
+// count); 2 leaf above the grid level owning a block of cells (same, depth in bits 24-29); 3 inner node (x = node).
 // Returns false if the walk does not apply (no seed, or too many cells) -- the caller then uses the climbing search.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int grid_cell_index(const NNArgs& A, double v, int a, int n) {
     double f = floor(dmul(dsub(v, A.gorg[a]), A.ginv));
     f = fmin(fmax(f, -1.0), (double)n);
     return (int)f;
+}
+
+__device__ __forceinline__ uint2 grid_entry(const NNArgs& A, int x, int y, int z) {
+    return __ldg(A.grid + ((long long)z * A.gny + y) * A.gnx + x);
 }
 
 template <int STRIDE>
@@ -310,25 +330,32 @@ __device__ __forceinline__ bool cell_walk(const NNArgs& A, const double qx, cons
         // no seed yet: locate q's own cell, follow q's path below it and take the points found there
         const int ix = grid_cell_index(A, qx, 0, A.gnx), iy = grid_cell_index(A, qy, 1, A.gny), iz = grid_cell_index(A, qz, 2, A.gnz);
         if (ix < 0 || iy < 0 || iz < 0 || ix >= A.gnx || iy >= A.gny || iz >= A.gnz) return false;
-        uint32_t n = __ldg(A.grid + ((long long)iz * A.gny + iy) * A.gnx + ix);
-        if (n == NONE) return false;
-        NodeRegs nd = load_node(A.nodes, n);
-        for (;;) {
-            const uint32_t mask = nd.meta & 0xFFu;
-            if (mask == 0u) break;
-            uint32_t oct = 0;
-            oct |= (qx > dmul(dadd(nd.lo[0], nd.hi[0]), 0.5)) ? 1u : 0u;
-            oct |= (qy > dmul(dadd(nd.lo[1], nd.hi[1]), 0.5)) ? 2u : 0u;
-            oct |= (qz > dmul(dadd(nd.lo[2], nd.hi[2]), 0.5)) ? 4u : 0u;
-            if (!((mask >> oct) & 1u)) break;
-            n = nd.child0 + __popc(mask & ((1u << oct) - 1u));
-            nd = load_node(A.nodes, n);
+        const uint2 e = grid_entry(A, ix, iy, iz);
+        const uint32_t kind = e.y >> 30;
+        if (kind == 0u) return false;
+        uint32_t pt0 = e.x, npts = e.y & 0xFFFFFFu;
+        if (kind == 3u) {
+            uint32_t n = e.x;
+            NodeRegs nd = load_node(A.nodes, n);
+            for (;;) {
+                const uint32_t mask = nd.meta & 0xFFu;
+                if (mask == 0u) break;
+                uint32_t oct = 0;
+                oct |= (qx > dmul(dadd(nd.lo[0], nd.hi[0]), 0.5)) ? 1u : 0u;
+                oct |= (qy > dmul(dadd(nd.lo[1], nd.hi[1]), 0.5)) ? 2u : 0u;
+                oct |= (qz > dmul(dadd(nd.lo[2], nd.hi[2]), 0.5)) ? 4u : 0u;
+                if (!((mask >> oct) & 1u)) break;
+                n = nd.child0 + __popc(mask & ((1u << oct) - 1u));
+                nd = load_node(A.nodes, n);
+            }
+            pt0 = nd.pt0;
+            npts = nd.npts;
         }
-        const uint32_t ns = nd.npts < (uint32_t)SEED_SCAN ? nd.npts : (uint32_t)SEED_SCAN;
+        const uint32_t ns = npts < (uint32_t)SEED_SCAN ? npts : (uint32_t)SEED_SCAN;
         for (uint32_t k = 0; k < ns; ++k) {
             double px, py, pz;
             uint32_t pidx;
-            load_point(A.pts, nd.pt0 + k, px, py, pz, pidx);
+            load_point(A.pts, pt0 + k, px, py, pz, pidx);
             Sd = fmin(Sd, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)));
         }
         if (!(Sd < 1e19)) return false;
@@ -349,19 +376,20 @@ __device__ __forceinline__ bool cell_walk(const NNArgs& A, const double qx, cons
     for (int z = z0; z <= z1; ++z)
         for (int y = y0; y <= y1; ++y)
             for (int x = x0; x <= x1; ++x) {
-                const uint32_t n = __ldg(A.grid + ((long long)z * A.gny + y) * A.gnx + x);
-                if (n == NONE) continue;
-                // a leaf shallower than the grid level owns a block of cells: search it once, from the first
-                // cell that the block and this query's range have in common
-                const NodeRegs nd = load_node(A.nodes, n);
-                const int d = (int)((nd.meta >> 8) & 0xFFu);
-                if (d < A.glevel) {
-                    const int bx = (int)floor(dmul(dsub(nd.lo[0], A.gorg[0]), A.ginv) + 0.5);
-                    const int by = (int)floor(dmul(dsub(nd.lo[1], A.gorg[1]), A.ginv) + 0.5);
-                    const int bz = (int)floor(dmul(dsub(nd.lo[2], A.gorg[2]), A.ginv) + 0.5);
-                    if (x != max(bx, x0) || y != max(by, y0) || z != max(bz, z0)) continue;
+                const uint2 en = grid_entry(A, x, y, z);
+                const uint32_t kind = en.y >> 30;
+                if (kind == 0u) continue;
+                if (kind == 3u) {
+                    fast_search<STRIDE>(A.nodes, A.pts, qx, qy, qz, en.x, F, stk);
+                    continue;
                 }
-                fast_search<STRIDE>(A.nodes, A.pts, qx, qy, qz, n, F, stk);
+                if (kind == 2u) {
+                    // a leaf above the grid level owns an aligned block of cells: scan it once, from the first cell
+                    // that the block and this query's range have in common
+                    const int sh = A.glevel - (int)((en.y >> 24) & 0x3Fu);
+                    if (x != max((x >> sh) << sh, x0) || y != max((y >> sh) << sh, y0) || z != max((z >> sh) << sh, z0)) continue;
+                }
+                scan_leaf_points(A.pts, en.x, en.y & 0xFFFFFFu, qx, qy, qz, F, NONE);
             }
     return true;
 }

@@ -12,8 +12,8 @@ timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; e
 if [ -s $OUT/${TAG}_bench.json ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
       python bench.py --no-cpu-baseline --no-e2e --steps 10 --warmup 3 > $OUT/${TAG}_ncu_list.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:nn_kernel --launch-skip 4 -c 2 \
-      -o $OUT/${TAG}_nn_full -f python bench.py --no-cpu-baseline --no-e2e --steps 3 --warmup 3 > $OUT/${TAG}_ncu_full.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:nn_kernel --launch-skip 6 -c 2 \
+      -o $OUT/${TAG}_nn_full -f python bench.py --no-cpu-baseline --no-e2e --steps 3 --warmup 5 > $OUT/${TAG}_ncu_full.log 2>&1
   ncu -i $OUT/${TAG}_nn_full.ncu-rep --page raw --csv > $OUT/${TAG}_nn_full_raw.csv 2>/dev/null
 fi
 ls -la $OUT | tail -20
