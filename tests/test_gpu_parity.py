@@ -344,3 +344,39 @@ def test_full_size_config2_properties(handle, oracle):
         handle.set_option("nn_mode", mode)
         idx0, dist0, _ = handle.nn_query(src)
         assert np.array_equal(idx0, idx) and np.array_equal(dist0, dist)
+
+
+def test_cpp_adapters_match_the_oracle(oracle, tmp_path):
+    """include/icp_b200_engine.hpp driven like the reference's callers drive the reference (tests/cpp/adapter_demo.cpp)."""
+    import json
+    import os
+    import subprocess
+    from iterativeclosestpoint_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "adapter_demo")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "adapter_demo.cpp"), "-o", exe,
+                           "-L", os.path.dirname(_lib.LIB_PATH), "-licp_b200", "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)])
+    src, tgt = synth.make_test_icp_pair(4000, seed=91)
+    sp, tp = str(tmp_path / "src.bin"), str(tmp_path / "tgt.bin")
+    tgt.tofile(tp)
+    # engine-shaped class
+    src.tofile(sp)
+    out = json.loads(subprocess.check_output([exe, "engine", sp, tp, "50", "1e-6"], text=True))
+    want = oracle.icp(src, tgt)
+    assert out["success"] and out["finished_ok"] and out["totalIterations"] == want.total_iterations
+    assert out["order"] == "s" + "ip" * want.total_iterations + "f"
+    assert abs(out["finalRMSE"] - want.final_rmse) <= REL_E2E * want.final_rmse
+    assert rel(np.array(out["finalR"]).reshape(3, 3), want.final_R) <= REL_E2E
+    moved = np.fromfile(sp + ".out").reshape(-1, 3)
+    assert np.max(np.abs(moved - want.source_out)) <= 1e-9 * float(np.max(np.abs(moved)))
+    # CLI-shaped function
+    src.tofile(sp)
+    out = json.loads(subprocess.check_output([exe, "cli", sp, tp, "20", "1e-2"], text=True))
+    want = oracle.icp(src, tgt, max_iterations=20, tolerance=1e-2, variant=1)
+    assert out["n_transforms"] == len(want.history)
+    assert rel(np.array(out["finalR"]).reshape(3, 3), want.final_R) <= REL_E2E
+    assert np.max(np.abs(np.array(out["finalT"]) - want.final_t)) <= REL_E2E
+    moved = np.fromfile(sp + ".out").reshape(-1, 3)
+    assert np.max(np.abs(moved - want.source_out)) <= 1e-9 * float(np.max(np.abs(moved)))
