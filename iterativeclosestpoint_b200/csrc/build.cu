@@ -467,6 +467,16 @@ __global__ void inv_perm_kernel(const TPoint* __restrict__ pts, int64_t n, uint3
     if (i < n) inv[(uint32_t)pts[i].idx] = (uint32_t)i;
 }
 
+// forget a tree's contents but keep its device buffers for the next build of this handle
+static void tree_reset(DeviceOctree& t) {
+    DeviceOctree keep;
+    keep.nodes = t.nodes; keep.parent = t.parent; keep.cell = t.cell; keep.cap_nodes = t.cap_nodes; keep.cap_cell = t.cap_cell;
+    keep.pts = t.pts; keep.cap_pts = t.cap_pts;
+    keep.inv_perm = t.inv_perm; keep.cap_inv = t.cap_inv;
+    keep.grid = t.grid; keep.cap_grid = t.cap_grid;
+    t = keep;
+}
+
 static void tree_free(DeviceOctree& t) {
     if (t.nodes) cudaFree(t.nodes);
     if (t.parent) cudaFree(t.parent);
@@ -483,7 +493,7 @@ void octree_free(Ctx* c) {
 }
 
 static int grow_nodes(Ctx* c, DeviceOctree& t, int64_t need) {
-    if (need <= t.cap_nodes) return ICP_OK;
+    if (need <= t.cap_nodes && (!t.want_cell || need <= t.cap_cell)) return ICP_OK;
     int64_t cap = std::max<int64_t>(need + need / 2, 1024);
     Node* nn = nullptr;
     uint32_t* np = nullptr;
@@ -504,6 +514,7 @@ static int grow_nodes(Ctx* c, DeviceOctree& t, int64_t need) {
     t.parent = np;
     t.cell = nc;
     t.cap_nodes = cap;
+    t.cap_cell = nc ? cap : 0;
     return ICP_OK;
 }
 
@@ -512,7 +523,7 @@ static int grow_nodes(Ctx* c, DeviceOctree& t, int64_t need) {
 // so its cells are cubes; it only has to bound its points (every point lies in the closed box of its leaf), not
 // to match anything in the reference.
 static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, int max_pts, int max_depth, bool cubic) {
-    tree_free(t);
+    tree_reset(t);  // keeps the device allocations of an earlier build (grow-only), forgets its contents
     t.want_cell = cubic;
     t.max_pts = max_pts;
     t.max_depth = max_depth;
@@ -549,7 +560,13 @@ static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, i
     if (key_bits > 0) ICPB_TRY(radix_sort_pairs(c, keys, keys_alt, idx, idx_alt, m, key_bits));
 
     // sorted points
-    ICPB_CUDA(c, cudaMalloc(&t.pts, (size_t)m * sizeof(TPoint)));
+    if (t.cap_pts < m) {
+        if (t.pts) ICPB_CUDA(c, cudaFree(t.pts));
+        t.pts = nullptr;
+        t.cap_pts = 0;
+        ICPB_CUDA(c, cudaMalloc(&t.pts, (size_t)m * sizeof(TPoint)));
+        t.cap_pts = m;
+    }
     uint32_t* d_misc = nullptr;  // [0] pos_of_idx0, [1] leaf counter, [2] scan total
     ICPB_TRY(devbuf_reserve(c, c->part_a, 4096));
     d_misc = (uint32_t*)c->part_a.p;
@@ -604,8 +621,15 @@ static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, i
 }
 
 static int build_inv_perm_of(Ctx* c, DeviceOctree& t) {
-    if (t.inv_perm) return ICP_OK;
-    ICPB_CUDA(c, cudaMalloc(&t.inv_perm, (size_t)t.n_pts * sizeof(uint32_t)));
+    if (t.inv_valid) return ICP_OK;
+    if (t.cap_inv < t.n_pts) {
+        if (t.inv_perm) ICPB_CUDA(c, cudaFree(t.inv_perm));
+        t.inv_perm = nullptr;
+        t.cap_inv = 0;
+        ICPB_CUDA(c, cudaMalloc(&t.inv_perm, (size_t)t.n_pts * sizeof(uint32_t)));
+        t.cap_inv = t.n_pts;
+    }
+    t.inv_valid = true;
     inv_perm_kernel<<<(int)((t.n_pts + 255) / 256), 256, 0, c->stream>>>(t.pts, t.n_pts, t.inv_perm);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
@@ -694,7 +718,13 @@ static int build_grid(Ctx* c, DeviceOctree& t) {
     t.gnz = (int)nz;
     t.grid_cell = cube / (double)(1ll << level);
     const size_t cells = (size_t)(nx * ny * nz);
-    ICPB_CUDA(c, cudaMalloc(&t.grid, cells * sizeof(uint2)));
+    if (t.cap_grid < (int64_t)cells) {
+        if (t.grid) ICPB_CUDA(c, cudaFree(t.grid));
+        t.grid = nullptr;
+        t.cap_grid = 0;
+        ICPB_CUDA(c, cudaMalloc(&t.grid, cells * sizeof(uint2)));
+        t.cap_grid = (int64_t)cells;
+    }
     ICPB_CUDA(c, cudaMemsetAsync(t.grid, 0, cells * sizeof(uint2), s));
     grid_fill_kernel<<<(int)((t.n_nodes + 127) / 128), 128, 0, s>>>(t.nodes, t.cell, t.n_nodes, level, t.gnx, t.gny, t.gnz, t.grid);
     c->launches++;
@@ -705,7 +735,8 @@ static int build_grid(Ctx* c, DeviceOctree& t) {
 // The reference's tree (c->tree: structure parity, literal traversal) and the isotropic search tree (c->fast: every
 // fast search path, and the canonical point order that match positions refer to).
 int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int max_depth) {
-    octree_free(c);
+    c->tree.valid = false;
+    c->fast.valid = false;
     c->prev_valid = false;
     if (m <= 0) return ICP_EMPTY_INPUT;
     if (max_depth < 0 || max_depth > 21 || m > 0x7fffffffLL) {

@@ -12,7 +12,8 @@ namespace icpb {
 struct DeviceOctree {
     Node* nodes = nullptr;
     uint32_t* parent = nullptr;  // parent node index per node (root: 0xFFFFFFFF)
-    int64_t n_nodes = 0, cap_nodes = 0;
+    int64_t n_nodes = 0, cap_nodes = 0, cap_cell = 0, cap_pts = 0, cap_inv = 0, cap_grid = 0;
+    bool inv_valid = false;
     TPoint* pts = nullptr;  // Morton-sorted target points (xyz + original index)
     int64_t n_pts = 0;
     int64_t n_leaves = 0;
