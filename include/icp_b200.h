@@ -102,6 +102,10 @@ typedef struct icp_octree_info {
     int32_t depth, max_points, max_depth, pad_;
     double root_lo[3], root_hi[3];
     float build_ms, pad2_;      /* device time of the last icp_octree_build (keys + sort + node table) */
+    /* the search structure built beside the reference tree: isotropic tree + pyramid of entry grids */
+    int64_t search_nodes, search_node_bytes, grid_bytes;
+    int32_t search_depth, grid_base_level, grid_fine_level, pad3_;
+    double grid_base_cell;      /* edge of a base-level cell, metres */
 } icp_octree_info;
 
 /* Callbacks replacing the engine's Qt signals (core/icpengine.h:70-75).  They fire on the calling thread,

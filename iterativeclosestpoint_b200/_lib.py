@@ -68,7 +68,10 @@ class IcpOctreeInfo(C.Structure):
     _fields_ = [("n_points", C.c_int64), ("n_nodes", C.c_int64), ("n_leaves", C.c_int64), ("node_bytes", C.c_int64),
                 ("point_bytes", C.c_int64), ("depth", C.c_int32), ("max_points", C.c_int32), ("max_depth", C.c_int32),
                 ("pad_", C.c_int32), ("root_lo", C.c_double * 3), ("root_hi", C.c_double * 3),
-                ("build_ms", C.c_float), ("pad2_", C.c_float)]
+                ("build_ms", C.c_float), ("pad2_", C.c_float),
+                ("search_nodes", C.c_int64), ("search_node_bytes", C.c_int64), ("grid_bytes", C.c_int64),
+                ("search_depth", C.c_int32), ("grid_base_level", C.c_int32), ("grid_fine_level", C.c_int32),
+                ("pad3_", C.c_int32), ("grid_base_cell", C.c_double)]
 
 
 ITERATION_CB = C.CFUNCTYPE(None, C.POINTER(IcpIteration), C.c_void_p)

@@ -511,7 +511,13 @@ int icp_set_option(icp_handle h, const char* key, double value) {
         c->prev_valid = false;
     }
     else if (!strcmp(key, "count")) c->opt_count = value != 0.0;
+    else if (!strcmp(key, "base_occupancy")) c->opt_base_occupancy = std::max(value, 1.0);
+    else if (!strcmp(key, "grid_levels")) c->opt_grid_levels = std::min(std::max((int)value, 1), 4);
+    else if (!strcmp(key, "range_max")) c->opt_range_max = std::max((int)value, 0);
+    else if (!strcmp(key, "walk_bias")) c->opt_walk_bias = (int)value;
+    else if (!strcmp(key, "search_depth")) c->opt_search_depth = std::min(std::max((int)value, 0), 21);
     else if (!strcmp(key, "grid_shift")) c->opt_grid_shift = (int)value;
+    else if (!strcmp(key, "grid_max_cells")) c->opt_grid_max_cells = std::max((long long)value, 1ll);
     else if (!strcmp(key, "walk_max_cells")) c->opt_walk_max_cells = std::max((int)value, 1);
     else if (!strcmp(key, "terminal_pts")) c->opt_terminal_pts = std::min(std::max((int)value, 1), 1024);
     else if (!strcmp(key, "search_leaf")) c->opt_search_leaf = std::min(std::max((int)value, 1), 1024);
@@ -613,6 +619,17 @@ int icp_octree_get_info(icp_handle h, icp_octree_info* info) {
         info->root_hi[a] = t.root_hi[a];
     }
     info->build_ms = c->last_build_ms;
+    const DeviceOctree& f = c->fast;
+    info->search_nodes = f.n_nodes;
+    info->search_node_bytes = f.n_nodes * (int64_t)sizeof(Node);
+    info->search_depth = f.depth;
+    info->grid_base_level = f.glev_min;
+    info->grid_fine_level = f.glev_min + f.glev_n - 1;
+    if (f.glev_n > 0) {
+        const int k = f.glev_n - 1;
+        info->grid_bytes = (f.goff[k] + (int64_t)f.gdim[k][0] * f.gdim[k][1] * f.gdim[k][2]) * (int64_t)sizeof(uint2);
+        info->grid_base_cell = f.cube / (double)(1ll << f.glev_min);
+    }
     return ICP_OK;
 }
 

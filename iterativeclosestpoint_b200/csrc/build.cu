@@ -648,10 +648,12 @@ __global__ void __launch_bounds__(256) leaf_depth_hist_kernel(const Node* __rest
     if (i >= n_nodes) return;
     const uint32_t meta = nodes[i].meta;
     if ((meta & 0xFFu) == 0u) atomicAdd(&hist[(meta >> 8) & 0x1Fu], (unsigned long long)nodes[i].npts);
+    atomicAdd(&hist[32 + ((meta >> 8) & 0x1Fu)], 1ull);                                 // nodes per depth
+    atomicAdd(&hist[64 + ((meta >> 8) & 0x1Fu)], (unsigned long long)nodes[i].npts);    // points that reach that depth
 }
 
 __global__ void __launch_bounds__(128) grid_fill_kernel(const Node* __restrict__ nodes, const uint64_t* __restrict__ cell,
-                                                        int64_t n_nodes, int level, int nx, int ny, int nz,
+                                                        int64_t n_nodes, int level, int nx, int ny, int nz, int range_max,
                                                         uint2* __restrict__ grid) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
@@ -659,14 +661,15 @@ __global__ void __launch_bounds__(128) grid_fill_kernel(const Node* __restrict__
     const int d = (int)((nd.meta >> 8) & 0xFFu);
     const bool leaf = (nd.meta & 0xFFu) == 0u;
     if (!(d == level || (leaf && d < level))) return;
-    // entry kinds, see nn_common.cuh (cell walk); a leaf with 2^24 points or more is entered through its node
+    // entry kinds, see nn_common.cuh (cell walk).  The points below any node are contiguous in the sorted order, so a
+    // cell with few points is entered as a plain range whether its node is a leaf or not; crowded cells keep the node.
     uint2 e;
-    if (leaf && nd.npts < (1u << 24))
+    if (nd.npts < (1u << 24) && (leaf || nd.npts <= (uint32_t)range_max))
         e = make_uint2(nd.pt0, nd.npts | ((uint32_t)d << 24) | ((d == level ? 1u : 2u) << 30));
     else if (d == level)
         e = make_uint2((uint32_t)i, 3u << 30);
     else
-        return;  // (cannot happen: a shallower leaf that large has max_depth < level)
+        return;
     const uint64_t pc = cell[i];
     const int sh = level - d;
     const long long x0 = (long long)(pc & 0x1FFFFFull) << sh, y0 = (long long)((pc >> 21) & 0x1FFFFFull) << sh,
@@ -680,54 +683,77 @@ __global__ void __launch_bounds__(128) grid_fill_kernel(const Node* __restrict__
 
 static int build_grid(Ctx* c, DeviceOctree& t) {
     cudaStream_t s = c->stream;
-    ICPB_TRY(devbuf_reserve(c, c->scratch0, 64 * sizeof(unsigned long long)));
+    ICPB_TRY(devbuf_reserve(c, c->scratch0, 96 * sizeof(unsigned long long)));
     unsigned long long* d_hist = (unsigned long long*)c->scratch0.p;
-    ICPB_CUDA(c, cudaMemsetAsync(d_hist, 0, 32 * sizeof(unsigned long long), s));
+    ICPB_CUDA(c, cudaMemsetAsync(d_hist, 0, 96 * sizeof(unsigned long long), s));
     leaf_depth_hist_kernel<<<(int)((t.n_nodes + 255) / 256), 256, 0, s>>>(t.nodes, t.n_nodes, d_hist);
     c->launches++;
-    unsigned long long hist[32];
+    unsigned long long hist[96];
     ICPB_CUDA(c, cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, s));
     ICPB_CUDA(c, cudaStreamSynchronize(s));
-    // level = the depth that holds the median point's leaf (cells there carry about one leaf of points) ...
-    unsigned long long acc = 0;
-    int level = 0;
-    for (int d = 0; d < 32; ++d) {
-        acc += hist[d];
-        if (2 * acc >= (unsigned long long)t.n_pts) {
-            level = d;
-            break;
-        }
+    // Levels by mean occupancy (points that reach a depth / nodes at that depth), among depths most points reach:
+    // the BASE level is the deepest one whose cells still hold several points (cheapest when the search ball is a good
+    // fraction of a cell); finer levels, down to ~1.5 points per cell, serve small balls (a converged registration).
+    int base = 0, fine = 0;
+    for (int d = 0; d <= 21; ++d) {
+        if (hist[32 + d] == 0) break;
+        if (2 * hist[64 + d] < (unsigned long long)t.n_pts) break;  // most points sit in shallower leaves
+        const double occ = (double)hist[64 + d] / (double)hist[32 + d];
+        if (occ >= c->opt_base_occupancy) base = d;
+        if (occ >= 1.5) fine = d;
     }
-    level = std::min(level + c->opt_grid_shift, 21);
-    level = std::max(level, 0);
-    // ... lowered until the dense array over the bounding box stays within the cell budget
-    const double cube = t.root_hi[0] - t.root_lo[0];
+    base = std::max(std::min(base + c->opt_grid_shift, 21), 0);
+    const int want_levels = std::min(std::max(c->opt_grid_levels, 1), 4);
+    fine = std::max(std::min(fine, base + want_levels - 1), base);
+    // ... all lowered until the pyramid of dense arrays over the bounding box stays within the entry budget
+    t.cube = t.root_hi[0] - t.root_lo[0];
     double ext[3];
     for (int a = 0; a < 3; ++a) ext[a] = c->tree.root_hi[a] - t.root_lo[a];  // the cloud's own extent (reference root box)
-    long long nx, ny, nz;
-    for (;; --level) {
-        const double g = cube / (double)(1ll << level);
-        nx = (long long)(ext[0] / g) + 1;
-        ny = (long long)(ext[1] / g) + 1;
-        nz = (long long)(ext[2] / g) + 1;
-        if ((double)nx * (double)ny * (double)nz <= (double)c->opt_grid_max_cells || level == 0) break;
+    auto dims = [&](int level, long long* n) {
+        const double g = t.cube / (double)(1ll << level);
+        double tot = 1.0;
+        for (int a = 0; a < 3; ++a) {
+            n[a] = (long long)(ext[a] / g) + 1;
+            tot *= (double)n[a];
+        }
+        return tot;
+    };
+    int nlev = 1;
+    for (;;) {
+        nlev = fine - base + 1;
+        double tot = 0.0;
+        long long n[3];
+        for (int k = 0; k < nlev; ++k) tot += dims(base + k, n);
+        if (tot <= (double)c->opt_grid_max_cells || fine == 0) break;
+        if (fine > base) --fine; else { --fine; --base; }
     }
-    t.grid_level = level;
-    t.gnx = (int)nx;
-    t.gny = (int)ny;
-    t.gnz = (int)nz;
-    t.grid_cell = cube / (double)(1ll << level);
-    const size_t cells = (size_t)(nx * ny * nz);
-    if (t.cap_grid < (int64_t)cells) {
+    base = std::max(base, 0);
+    fine = std::max(fine, base);
+    nlev = fine - base + 1;
+    t.glev_n = nlev;
+    t.glev_min = base;
+    long long total = 0;
+    for (int k = 0; k < nlev; ++k) {
+        long long n[3];
+        dims(t.glev_min + k, n);
+        t.goff[k] = total;
+        for (int a = 0; a < 3; ++a) t.gdim[k][a] = (int)n[a];
+        total += n[0] * n[1] * n[2];
+    }
+    if (t.cap_grid < total) {
         if (t.grid) ICPB_CUDA(c, cudaFree(t.grid));
         t.grid = nullptr;
         t.cap_grid = 0;
-        ICPB_CUDA(c, cudaMalloc(&t.grid, cells * sizeof(uint2)));
-        t.cap_grid = (int64_t)cells;
+        ICPB_CUDA(c, cudaMalloc(&t.grid, (size_t)total * sizeof(uint2)));
+        t.cap_grid = total;
     }
-    ICPB_CUDA(c, cudaMemsetAsync(t.grid, 0, cells * sizeof(uint2), s));
-    grid_fill_kernel<<<(int)((t.n_nodes + 127) / 128), 128, 0, s>>>(t.nodes, t.cell, t.n_nodes, level, t.gnx, t.gny, t.gnz, t.grid);
-    c->launches++;
+    ICPB_CUDA(c, cudaMemsetAsync(t.grid, 0, (size_t)total * sizeof(uint2), s));
+    for (int k = 0; k < nlev; ++k) {
+        grid_fill_kernel<<<(int)((t.n_nodes + 127) / 128), 128, 0, s>>>(t.nodes, t.cell, t.n_nodes, t.glev_min + k, t.gdim[k][0],
+                                                                        t.gdim[k][1], t.gdim[k][2], c->opt_range_max,
+                                                                        t.grid + t.goff[k]);
+        c->launches++;
+    }
     ICPB_CUDA(c, cudaGetLastError());
     return ICP_OK;
 }
@@ -744,7 +770,7 @@ int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int
         return ICP_INVALID_ARGUMENT;
     }
     ICPB_TRY(build_tree(c, c->tree, d_xyz, m, max_pts, max_depth, false));
-    ICPB_TRY(build_tree(c, c->fast, d_xyz, m, c->opt_search_leaf, 21, true));
+    ICPB_TRY(build_tree(c, c->fast, d_xyz, m, c->opt_search_leaf, c->opt_search_depth, true));
     ICPB_TRY(build_inv_perm_of(c, c->fast));  // original index -> search-tree position (literal results, stage API)
     ICPB_TRY(build_grid(c, c->fast));
     return ICP_OK;

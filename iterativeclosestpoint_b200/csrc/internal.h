@@ -25,9 +25,11 @@ struct DeviceOctree {
     // search tree only: integer cell coordinates per node and the dense entry grid at level grid_level
     bool want_cell = false;
     uint64_t* cell = nullptr;
-    uint2* grid = nullptr;
-    int grid_level = 0, gnx = 0, gny = 0, gnz = 0;
-    double grid_cell = 0.0;
+    uint2* grid = nullptr;            // pyramid of dense entry grids, levels glev_min .. glev_min + glev_n - 1
+    int glev_min = 0, glev_n = 0;
+    long long goff[4] = {0, 0, 0, 0};
+    int gdim[4][3] = {};
+    double cube = 0.0;                // edge of the cubic root
     bool valid = false;
 };
 
@@ -54,10 +56,15 @@ struct Ctx {
 
     DeviceOctree tree;  // the reference's octree (structure parity, literal traversal)
     DeviceOctree fast;  // isotropic search tree over the same points; match positions index ITS point order
-    int opt_search_leaf = 16;        // leaf capacity of the search tree
+    int opt_search_leaf = 4;         // leaf capacity of the search tree
+    int opt_search_depth = 21;       // depth cap of the search tree
     int opt_terminal_pts = 16;       // tile kernel stages subtrees up to this size whole
     int opt_grid_shift = 0;          // entry grid level relative to the median leaf depth
-    long long opt_grid_max_cells = 1ll << 26;
+    long long opt_grid_max_cells = 1ll << 28;  // entries (8 B each) over the whole pyramid
+    int opt_grid_levels = 3;         // pyramid height (base level + finer ones)
+    double opt_base_occupancy = 4.0; // mean points per occupied cell the base level must still have
+    int opt_range_max = 64;          // inner cells up to this many points are entered as plain point ranges
+    int opt_walk_bias = -2;          // cell walk: levels finer (+) or coarser (-) than 'cell >= ball box'
     int opt_walk_max_cells = 27;     // cell walk gives way to the climbing search beyond this many cells
     DevBuf tgt_raw;  // original-order target AoS (kept for the stage API)
     int64_t n_tgt = 0;

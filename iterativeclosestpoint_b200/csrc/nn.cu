@@ -125,14 +125,19 @@ int nn_launch(Ctx* c, const NNLaunch& L) {
     A.rpts = c->tree.pts;
     A.inv = c->fast.inv_perm;
     A.grid = c->fast.grid;
-    A.gnx = c->fast.gnx;
-    A.gny = c->fast.gny;
-    A.gnz = c->fast.gnz;
-    A.glevel = c->fast.grid_level;
+    A.glmin = c->fast.glev_min;
+    A.gnlev = c->fast.glev_n;
     A.gmax_cells = c->opt_walk_max_cells;
+    A.gbias = c->opt_walk_bias;
+    A.gcube = c->fast.cube;
+    for (int k = 0; k < 4; ++k) {
+        A.goff[k] = c->fast.goff[k];
+        for (int a = 0; a < 3; ++a) A.gdim[k][a] = c->fast.gdim[k][a];
+        A.ginv[k] = (k < c->fast.glev_n) ? (double)(1ll << (c->fast.glev_min + k)) / c->fast.cube : 0.0;
+    }
     for (int a = 0; a < 3; ++a) A.gorg[a] = c->fast.root_lo[a];
-    A.ginv = 1.0 / c->fast.grid_cell;
-    A.geps = c->fast.grid_cell * 9.5367431640625e-07;  // cell * 2^-20 >> any rounding of the bisection boundaries
+    // finest cell * 2^-20 >> any rounding of the bisection boundaries
+    A.geps = c->fast.cube / (double)(1ll << (c->fast.glev_min + c->fast.glev_n - 1)) * 9.5367431640625e-07;
     A.sx = L.sx; A.sy = L.sy; A.sz = L.sz;
     A.ox = L.ox; A.oy = L.oy; A.oz = L.oz;
     A.n = L.n;

@@ -17,9 +17,12 @@ struct NNArgs {
     const TPoint* __restrict__ rpts;
     const uint32_t* __restrict__ inv;  // original target index -> position in `pts`
     // entry grid of the search tree (build.cu): cell -> owning node, NONE where empty
-    const uint2* __restrict__ grid;
-    int gnx, gny, gnz, glevel, gmax_cells;
-    double gorg[3], ginv, geps;
+    const uint2* __restrict__ grid;    // pyramid: levels glmin .. glmin + gnlev - 1, level k at grid + goff[k]
+    int glmin, gnlev, gmax_cells, gbias;
+    long long goff[4];
+    int gdim[4][3];
+    double ginv[4];                    // 1 / cell edge per level
+    double gorg[3], geps, gcube;
     const double* sx;
     const double* sy;
     const double* sz;
@@ -313,24 +316,66 @@ __device__ __forceinline__ void fast_search(const Node* __restrict__ nodes, cons
 // count); 2 leaf above the grid level owning a block of cells (same, depth in bits 24-29); 3 inner node (x = node).
 // Returns false if the walk does not apply (no seed, or too many cells) -- the caller then uses the climbing search.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int grid_cell_index(const NNArgs& A, double v, int a, int n) {
-    double f = floor(dmul(dsub(v, A.gorg[a]), A.ginv));
+struct GridView {
+    const uint2* g;
+    int nx, ny, nz, level;
+    double inv;
+};
+
+__device__ __forceinline__ GridView grid_view(const NNArgs& A, int k) {
+    GridView V;
+    V.g = A.grid + A.goff[k];
+    V.nx = A.gdim[k][0];
+    V.ny = A.gdim[k][1];
+    V.nz = A.gdim[k][2];
+    V.level = A.glmin + k;
+    V.inv = A.ginv[k];
+    return V;
+}
+
+// finest pyramid level whose cell edge is at least w (so a box of width w meets at most 2 cells per axis), + bias
+__device__ __forceinline__ int grid_level_for_width(const NNArgs& A, double w, int bias) {
+    int l = A.glmin + A.gnlev - 1;
+    if (w > 0.0) {
+        const double ratio = A.gcube / w;  // floor(log2(ratio)) from the exponent field
+        const int ex = ((__double2hiint(ratio) >> 20) & 0x7FF) - 1023;
+        l = min(l, ex + bias);
+    }
+    l = max(l, A.glmin);
+    return l - A.glmin;
+}
+
+__device__ __forceinline__ int grid_cell_index(const NNArgs& A, const GridView& V, double v, int a, int n) {
+    double f = floor(dmul(dsub(v, A.gorg[a]), V.inv));
     f = fmin(fmax(f, -1.0), (double)n);
     return (int)f;
 }
 
-__device__ __forceinline__ uint2 grid_entry(const NNArgs& A, int x, int y, int z) {
-    return __ldg(A.grid + ((long long)z * A.gny + y) * A.gnx + x);
+__device__ __forceinline__ uint2 grid_entry(const GridView& V, int x, int y, int z) {
+    return __ldg(V.g + ((long long)z * V.ny + y) * V.nx + x);
 }
 
 template <int STRIDE>
 __device__ __forceinline__ bool cell_walk(const NNArgs& A, const double qx, const double qy, const double qz, double Sd,
                                           uint2* stk, Fast& F) {
     if (!(Sd < 1e19)) {
-        // no seed yet: locate q's own cell, follow q's path below it and take the points found there
-        const int ix = grid_cell_index(A, qx, 0, A.gnx), iy = grid_cell_index(A, qy, 1, A.gny), iz = grid_cell_index(A, qz, 2, A.gnz);
-        if (ix < 0 || iy < 0 || iz < 0 || ix >= A.gnx || iy >= A.gny || iz >= A.gnz) return false;
-        const uint2 e = grid_entry(A, ix, iy, iz);
+        // no seed yet: take the points of q's own base-level cell (clamped into the grid, so queries outside the
+        // cloud's box get a seed too); if that cell is empty try its six face neighbours.  Any real target point
+        // is a valid seed -- a closer one only makes the walk cheaper.
+        const GridView V0 = grid_view(A, 0);
+        int ix = grid_cell_index(A, V0, qx, 0, V0.nx), iy = grid_cell_index(A, V0, qy, 1, V0.ny), iz = grid_cell_index(A, V0, qz, 2, V0.nz);
+        ix = min(max(ix, 0), V0.nx - 1);
+        iy = min(max(iy, 0), V0.ny - 1);
+        iz = min(max(iz, 0), V0.nz - 1);
+        uint2 e = make_uint2(0u, 0u);
+#pragma unroll 1
+        for (int t = 0; t < 7; ++t) {
+            const int dz = (t == 1) ? -1 : (t == 2) ? 1 : 0, dy = (t == 3) ? -1 : (t == 4) ? 1 : 0, dx = (t == 5) ? -1 : (t == 6) ? 1 : 0;
+            const int x = ix + dx, y = iy + dy, z = iz + dz;
+            if (x < 0 || y < 0 || z < 0 || x >= V0.nx || y >= V0.ny || z >= V0.nz) continue;
+            e = grid_entry(V0, x, y, z);
+            if ((e.y >> 30) != 0u) break;
+        }
         const uint32_t kind = e.y >> 30;
         if (kind == 0u) return false;
         uint32_t pt0 = e.x, npts = e.y & 0xFFFFFFu;
@@ -339,7 +384,7 @@ __device__ __forceinline__ bool cell_walk(const NNArgs& A, const double qx, cons
             NodeRegs nd = load_node(A.nodes, n);
             for (;;) {
                 const uint32_t mask = nd.meta & 0xFFu;
-                if (mask == 0u) break;
+                if (mask == 0u || nd.npts <= 32u) break;
                 uint32_t oct = 0;
                 oct |= (qx > dmul(dadd(nd.lo[0], nd.hi[0]), 0.5)) ? 1u : 0u;
                 oct |= (qy > dmul(dadd(nd.lo[1], nd.hi[1]), 0.5)) ? 2u : 0u;
@@ -351,46 +396,77 @@ __device__ __forceinline__ bool cell_walk(const NNArgs& A, const double qx, cons
             pt0 = nd.pt0;
             npts = nd.npts;
         }
-        const uint32_t ns = npts < (uint32_t)SEED_SCAN ? npts : (uint32_t)SEED_SCAN;
-        for (uint32_t k = 0; k < ns; ++k) {
-            double px, py, pz;
-            uint32_t pidx;
-            load_point(A.pts, pt0 + k, px, py, pz, pidx);
-            Sd = fmin(Sd, sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz)));
+        const uint32_t ns = npts < 32u ? npts : 32u;
+        for (uint32_t k = 0; k < ns; k += 4) {
+            double px[4], py[4], pz[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t kk = (k + j < ns) ? k + j : ns - 1u;
+                uint32_t pidx;
+                load_point(A.pts, pt0 + kk, px[j], py[j], pz[j], pidx);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Sd = fmin(Sd, sumsq3(dsub(px[j], qx), dsub(py[j], qy), dsub(pz[j], qz)));
         }
         if (!(Sd < 1e19)) return false;
     }
     const double r = dmul(dsqrt(Sd), 1.0 + 9.5367431640625e-07);  // sqrt(S) (1 + 2^-20)
     const double e = dadd(r, A.geps);
-    int x0 = grid_cell_index(A, dsub(qx, e), 0, A.gnx), x1 = grid_cell_index(A, dadd(qx, e), 0, A.gnx);
-    int y0 = grid_cell_index(A, dsub(qy, e), 1, A.gny), y1 = grid_cell_index(A, dadd(qy, e), 1, A.gny);
-    int z0 = grid_cell_index(A, dsub(qz, e), 2, A.gnz), z1 = grid_cell_index(A, dadd(qz, e), 2, A.gnz);
+    const GridView V = grid_view(A, grid_level_for_width(A, dmul(e, 2.0), A.gbias));
+    int x0 = grid_cell_index(A, V, dsub(qx, e), 0, V.nx), x1 = grid_cell_index(A, V, dadd(qx, e), 0, V.nx);
+    int y0 = grid_cell_index(A, V, dsub(qy, e), 1, V.ny), y1 = grid_cell_index(A, V, dadd(qy, e), 1, V.ny);
+    int z0 = grid_cell_index(A, V, dsub(qz, e), 2, V.nz), z1 = grid_cell_index(A, V, dadd(qz, e), 2, V.nz);
     x0 = max(x0, 0); y0 = max(y0, 0); z0 = max(z0, 0);
-    x1 = min(x1, A.gnx - 1); y1 = min(y1, A.gny - 1); z1 = min(z1, A.gnz - 1);
+    x1 = min(x1, V.nx - 1); y1 = min(y1, V.ny - 1); z1 = min(z1, V.nz - 1);
     if ((long long)(x1 - x0 + 1) * (long long)(y1 - y0 + 1) * (long long)(z1 - z0 + 1) > (long long)A.gmax_cells) return false;
     F.best = ICPB_INF;
     F.second = ICPB_INF;
     F.pos = NONE;
     F.node = NONE;
     F.bound = dmul(Sd, 1.0 + 1.8189894035458565e-12);  // S (1 + 2^-39)
-    for (int z = z0; z <= z1; ++z)
-        for (int y = y0; y <= y1; ++y)
-            for (int x = x0; x <= x1; ++x) {
-                const uint2 en = grid_entry(A, x, y, z);
-                const uint32_t kind = en.y >> 30;
-                if (kind == 0u) continue;
-                if (kind == 3u) {
-                    fast_search<STRIDE>(A.nodes, A.pts, qx, qy, qz, en.x, F, stk);
-                    continue;
-                }
-                if (kind == 2u) {
-                    // a leaf above the grid level owns an aligned block of cells: scan it once, from the first cell
-                    // that the block and this query's range have in common
-                    const int sh = A.glevel - (int)((en.y >> 24) & 0x3Fu);
-                    if (x != max((x >> sh) << sh, x0) || y != max((y >> sh) << sh, y0) || z != max((z >> sh) << sh, z0)) continue;
-                }
-                scan_leaf_points(A.pts, en.x, en.y & 0xFFFFFFu, qx, qy, qz, F, NONE);
+    // One flat loop over (cell, point batch): a lane that has used up its leaf advances to its next non-empty cell
+    // while the others wait, then all lanes scan a batch together -- the warp's trip count follows the lane with the
+    // most POINTS, not (most cells) x (largest leaf).
+    const int nxr = x1 - x0 + 1, nyr = y1 - y0 + 1;
+    const int ncell = nxr * nyr * (z1 - z0 + 1);
+    int c = -1;
+    uint32_t pt0 = 0, npts = 0, k = 0;
+    for (;;) {
+        while (k >= npts) {
+            if (++c >= ncell) break;
+            const int x = x0 + c % nxr, y = y0 + (c / nxr) % nyr, z = z0 + c / (nxr * nyr);
+            const uint2 en = grid_entry(V, x, y, z);
+            const uint32_t kind = en.y >> 30;
+            if (kind == 0u) continue;
+            if (kind == 3u) {
+                fast_search<STRIDE>(A.nodes, A.pts, qx, qy, qz, en.x, F, stk);
+                continue;
             }
+            if (kind == 2u) {
+                // a leaf above the grid level owns an aligned block of cells: scan it once, from the first cell
+                // that the block and this query's range have in common
+                const int sh = V.level - (int)((en.y >> 24) & 0x3Fu);
+                if (x != max((x >> sh) << sh, x0) || y != max((y >> sh) << sh, y0) || z != max((z >> sh) << sh, z0)) continue;
+            }
+            pt0 = en.x;
+            npts = en.y & 0xFFFFFFu;
+            k = 0;
+        }
+        if (c >= ncell) break;
+        double px[4], py[4], pz[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t kk = (k + j < npts) ? k + j : npts - 1u;
+            uint32_t pidx;
+            load_point(A.pts, pt0 + kk, px[j], py[j], pz[j], pidx);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double s = sumsq3(dsub(px[j], qx), dsub(py[j], qy), dsub(pz[j], qz));
+            if (k + j < npts && s <= F.bound) fast_take(F, s, pt0 + k + j, NONE);
+        }
+        k += 4;
+    }
     return true;
 }
 

@@ -28,6 +28,8 @@ constexpr int STK_SOFT = 224;              // batch pops keep the node stack bel
 constexpr int STK_ALLOC = 384;             // ... single pops can add 7 per level on top (7 * 22 = 154)
 constexpr int TERMINAL_PTS = 16;           // subtrees with at most this many points are staged whole
 constexpr int MAX_PASSES = 3;
+constexpr int TILE_MAX_CELLS = 160;        // boxes meeting more grid cells are collected through the tree
+static_assert(TILE_MAX_CELLS + 32 <= STK_SOFT, "every over-full cell of a tile must fit on the node stack");
 constexpr int CAND_BUDGET = 8192;          // a pass that would stage more than this gives the tile up
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -170,8 +172,32 @@ __global__ void __launch_bounds__(TILE_THREADS, 6) nn_tile_kernel(const NNArgs A
             ehi[a] = bh[a] + r_tile;
         }
         ++dbg_passes;
-        // ---- start node: smallest subtree that holds every leaf meeting E (all lanes walk together) -----------
-        {
+        // ---- where the candidates come from: the entry-grid cells that E meets (one 8-byte entry per lane per round);
+        //      a box that meets too many cells is collected through the tree instead, from the smallest subtree
+        //      that holds every leaf meeting E (all lanes walk together)
+        int gx0 = 0, gy0 = 0, gz0 = 0, gnxr = 0, gnyr = 0, ncell = 0;
+        bool use_grid = false;
+        GridView V = grid_view(A, 0);
+        if (A.grid != nullptr) {
+            // finest level at which E still meets few enough cells
+            for (int k = A.gnlev - 1; k >= 0 && !use_grid; --k) {
+                V = grid_view(A, k);
+                int x0 = grid_cell_index(A, V, elo[0] - A.geps, 0, V.nx), x1 = grid_cell_index(A, V, ehi[0] + A.geps, 0, V.nx);
+                int y0 = grid_cell_index(A, V, elo[1] - A.geps, 1, V.ny), y1 = grid_cell_index(A, V, ehi[1] + A.geps, 1, V.ny);
+                int z0 = grid_cell_index(A, V, elo[2] - A.geps, 2, V.nz), z1 = grid_cell_index(A, V, ehi[2] + A.geps, 2, V.nz);
+                x0 = max(x0, 0); y0 = max(y0, 0); z0 = max(z0, 0);
+                x1 = min(x1, V.nx - 1); y1 = min(y1, V.ny - 1); z1 = min(z1, V.nz - 1);
+                const long long nc = (long long)max(x1 - x0 + 1, 0) * (long long)max(y1 - y0 + 1, 0) * (long long)max(z1 - z0 + 1, 0);
+                if (nc <= (long long)TILE_MAX_CELLS) {
+                    use_grid = true;
+                    gx0 = x0; gy0 = y0; gz0 = z0;
+                    gnxr = x1 - x0 + 1;
+                    gnyr = y1 - y0 + 1;
+                    ncell = (int)nc;
+                }
+            }
+        }
+        if (!use_grid) {
             uint32_t n = start_node;
             NodeRegs nd;
             for (;;) {
@@ -198,15 +224,46 @@ __global__ void __launch_bounds__(TILE_THREADS, 6) nn_tile_kernel(const NNArgs A
         best = ICPB_INF;
         second = ICPB_INF;
         bpos = NONE;
-        int S = 1, count = 0, total = 0;
+        int S = use_grid ? 0 : 1, count = 0, total = 0, cell_base = 0;
         bool aborted = false;
         uint32_t pend_pt0 = 0;
         int pend_n = 0;
-        if (lane == 0) stk[0] = start_node;
+        if (lane == 0 && !use_grid) stk[0] = start_node;
         __syncwarp();
         for (;;) {
             if (!__any_sync(FULL, pend_n > 0)) {
-                if (S == 0) {
+                if (cell_base < ncell) {
+                    // next 32 grid cells, one per lane
+                    const int cc = cell_base + lane;
+                    cell_base += 32;
+                    uint32_t push = NONE;
+                    if (cc < ncell) {
+                        const int x = gx0 + cc % gnxr, y = gy0 + (cc / gnxr) % gnyr, z = gz0 + cc / (gnxr * gnyr);
+                        const uint2 en = grid_entry(V, x, y, z);
+                        const uint32_t kind = en.y >> 30;
+                        bool take = kind == 1u;
+                        if (kind == 2u) {  // a shallower leaf owns a block of cells: take it at the first cell shared with the range
+                            const int sh = V.level - (int)((en.y >> 24) & 0x3Fu);
+                            take = x == max((x >> sh) << sh, gx0) && y == max((y >> sh) << sh, gy0) && z == max((z >> sh) << sh, gz0);
+                        }
+                        if (take) {
+                            pend_pt0 = en.x;
+                            pend_n = (int)(en.y & 0xFFFFFFu);
+                        }
+                        if (kind == 3u) push = en.x;  // over-full cell: expand its node below
+                    }
+                    const unsigned pm = __ballot_sync(FULL, push != NONE);
+                    if (push != NONE) stk[S + __popc(pm & ((1u << lane) - 1u))] = push;
+                    S += __popc(pm);
+                    ++dbg_rounds;
+                    const int pincl = wscan_incl(pend_n, lane);
+                    total += __shfl_sync(FULL, pincl, 31);
+                    __syncwarp();
+                    if (total > CAND_BUDGET) {
+                        aborted = true;
+                        break;
+                    }
+                } else if (S == 0) {
                     if (count == 0) break;
                 } else {
                     // pop up to 32 nodes, one per lane
@@ -272,7 +329,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 6) nn_tile_kernel(const NNArgs A
                 count += tot < room ? tot : room;
                 __syncwarp();
             }
-            if (__any_sync(FULL, pend_n > 0) || S == 0) {
+            if (__any_sync(FULL, pend_n > 0) || (S == 0 && cell_base >= ncell)) {
                 // every lane scans every staged point: uniform control flow, broadcast reads
 #pragma unroll 4
                 for (int c = 0; c < count; ++c) {
