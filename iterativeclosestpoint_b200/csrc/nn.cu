@@ -71,14 +71,22 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
             pp = A.prev_pos[i];
         }
         uint32_t result_node = NONE;
-        const uint32_t result = per_thread_query<NN_THREADS>(A, qx, qy, qz, finite_q, pp, pn, ICPB_INF, stk, result_node, fell_back);
+        double best_s;
+        const uint32_t result = per_thread_query<NN_THREADS>(A, qx, qy, qz, finite_q, pp, pn, ICPB_INF, stk, result_node, fell_back,
+                                                             false, &best_s);
         // findNearest returns index 0 when nothing was accepted (best_idx = 0 initially, octree.cpp:179)
         const uint32_t pos = (result == NONE) ? A.pos_of_idx0 : result;
-        double px, py, pz;
-        uint32_t pidx;
-        load_point(A.pts, pos, px, py, pz, pidx);
-        // computeDistance(p_src, p_tgt) (icpengine.cpp:68-74)
-        const double d = dsqrt(sumsq3(dsub(qx, px), dsub(qy, py), dsub(qz, pz)));
+        // computeDistance(p_src, p_tgt) (icpengine.cpp:68-74) = sqrt(dx*dx + dy*dy + dz*dz) with d = src - tgt; the search
+        // evaluated the same sum with d = tgt - src, whose squares are the same doubles, so its value is reused.
+        double d;
+        if (best_s >= 0.0) {
+            d = dsqrt(best_s);
+        } else {
+            double px, py, pz;
+            uint32_t pidx;
+            load_point(A.pts, pos, px, py, pz, pidx);
+            d = dsqrt(sumsq3(dsub(qx, px), dsub(qy, py), dsub(qz, pz)));
+        }
         A.pos_out[i] = pos;
         if (A.node_io) A.node_io[i] = result_node;
         A.dist_out[i] = d;

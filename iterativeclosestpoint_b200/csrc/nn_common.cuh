@@ -427,14 +427,22 @@ __device__ __forceinline__ bool cell_walk(const NNArgs& A, const double qx, cons
     // One flat loop over (cell, point batch): a lane that has used up its leaf advances to its next non-empty cell
     // while the others wait, then all lanes scan a batch together -- the warp's trip count follows the lane with the
     // most POINTS, not (most cells) x (largest leaf).
-    const int nxr = x1 - x0 + 1, nyr = y1 - y0 + 1;
-    const int ncell = nxr * nyr * (z1 - z0 + 1);
-    int c = -1;
+    if (x1 < x0 || y1 < y0 || z1 < z0) return true;  // the ball misses the grid: nothing found, the caller falls back
+    int x = x0 - 1, y = y0, z = z0;       // cell cursor (x fastest)
+    bool more = true;
     uint32_t pt0 = 0, npts = 0, k = 0;
     for (;;) {
         while (k >= npts) {
-            if (++c >= ncell) break;
-            const int x = x0 + c % nxr, y = y0 + (c / nxr) % nyr, z = z0 + c / (nxr * nyr);
+            if (++x > x1) {
+                x = x0;
+                if (++y > y1) {
+                    y = y0;
+                    if (++z > z1) {
+                        more = false;
+                        break;
+                    }
+                }
+            }
             const uint2 en = grid_entry(V, x, y, z);
             const uint32_t kind = en.y >> 30;
             if (kind == 0u) continue;
@@ -452,7 +460,7 @@ __device__ __forceinline__ bool cell_walk(const NNArgs& A, const double qx, cons
             npts = en.y & 0xFFFFFFu;
             k = 0;
         }
-        if (c >= ncell) break;
+        if (!more) break;
         double px[4], py[4], pz[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -480,9 +488,10 @@ template <int STRIDE>
 __device__ __forceinline__ uint32_t per_thread_query(const NNArgs& A, const double qx, const double qy, const double qz,
                                                      const bool finite_q, const uint32_t pp, const uint32_t pn,
                                                      const double extra_seed, uint2* stk, uint32_t& result_node,
-                                                     bool& fell_back, const bool skip_fast = false) {
+                                                     bool& fell_back, const bool skip_fast = false, double* best_s = nullptr) {
     uint32_t result = NONE;
     result_node = NONE;
+    if (best_s) *best_s = -1.0;  // set to s(answer) when a fast path produced the answer (computeDistance = sqrt of it)
     bool need_literal = finite_q;
     bool walked = false;
     if (A.mode == 3 && finite_q && !skip_fast) {
@@ -499,6 +508,7 @@ __device__ __forceinline__ uint32_t per_thread_query(const NNArgs& A, const doub
             result = F.pos;
             result_node = F.node;
             need_literal = false;
+            if (best_s) *best_s = F.best;
         }
     }
     if (A.mode >= 1 && finite_q && !skip_fast && !walked) {
@@ -613,6 +623,7 @@ __device__ __forceinline__ uint32_t per_thread_query(const NNArgs& A, const doub
                 result = F.pos;
                 result_node = F.node;
                 need_literal = false;
+                if (best_s) *best_s = F.best;
             }
         }
     }
