@@ -10,7 +10,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
 #include <new>
+#include <thread>
 
 namespace icpb {
 
@@ -452,6 +454,8 @@ void icp_destroy(icp_handle h) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     icp_comm_destroy(h);
+    for (Ctx* w : c->workers) icp_destroy((icp_handle)w);
+    c->workers.clear();
     octree_free(c);
     DevBuf* bufs[] = {&c->tgt_raw, &c->sx, &c->sy, &c->sz, &c->sperm, &c->pos, &c->dist, &c->mask, &c->part_a, &c->part_b,
                       &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io};
@@ -511,6 +515,7 @@ int icp_set_option(icp_handle h, const char* key, double value) {
         c->prev_valid = false;
     }
     else if (!strcmp(key, "count")) c->opt_count = value != 0.0;
+    else if (!strcmp(key, "batch_workers")) c->opt_batch_workers = std::min(std::max((int)value, 1), 64);
     else if (!strcmp(key, "base_occupancy")) c->opt_base_occupancy = std::max(value, 1.0);
     else if (!strcmp(key, "grid_levels")) c->opt_grid_levels = std::min(std::max((int)value, 1), 4);
     else if (!strcmp(key, "range_max")) c->opt_range_max = std::max((int)value, 0);
@@ -905,17 +910,53 @@ int icp_comm_destroy(icp_handle h) {
 }
 
 // ---- batch (BASELINE.json config #5) -------------------------------------------------------------------
+// Many small independent registrations: each is launch- and latency-bound on its own (a 2k-point pair keeps a
+// fraction of one SM busy), so the batch is spread over a pool of worker handles -- one CUDA stream each on the
+// same device, driven by one host thread each -- and the GPU overlaps their kernels.  Every pair goes through the
+// ordinary single-pair path (register_impl), so batch results are the single-pair results by construction.
 int icp_register_batch(icp_handle h, int32_t n_pairs, double* const* src_xyz, const int64_t* n_src, const double* const* tgt_xyz,
                        const int64_t* n_tgt, icp_result* results) {
     Ctx* c = (Ctx*)h;
     if (!c || n_pairs < 0 || (n_pairs > 0 && (!src_xyz || !n_src || !tgt_xyz || !n_tgt || !results))) return ICP_INVALID_ARGUMENT;
-    int worst = ICP_OK;
-    for (int32_t p = 0; p < n_pairs; ++p) {
-        int s = register_impl(c, src_xyz[p], n_src[p], n_src[p], tgt_xyz[p], n_tgt[p], &results[p], nullptr);
-        if (s == ICP_CUDA_ERROR || s == ICP_NCCL_ERROR) return s;
-        if (s != ICP_OK && worst == ICP_OK) worst = s;
+    if (n_pairs == 0) return ICP_OK;
+    const int want = std::max(1, std::min(std::min(c->opt_batch_workers, (int)n_pairs), 64));
+    while ((int)c->workers.size() < want) {
+        icp_handle w = nullptr;
+        if (icp_create(&w, c->device) != ICP_OK) {
+            c->err = "batch: could not create a worker handle";
+            return ICP_CUDA_ERROR;
+        }
+        c->workers.push_back((Ctx*)w);
     }
-    return worst;
+    std::atomic<int32_t> next{0};
+    std::atomic<int> fatal{ICP_OK}, worst{ICP_OK};
+    auto run = [&](Ctx* w) {
+        cudaSetDevice(w->device);
+        w->params = c->params;
+        w->opt_nn_mode = c->opt_nn_mode;
+        w->opt_order_queries = c->opt_order_queries;
+        for (;;) {
+            const int32_t p = next.fetch_add(1);
+            if (p >= n_pairs || fatal.load() != ICP_OK) break;
+            const int s = register_impl(w, src_xyz[p], n_src[p], n_src[p], tgt_xyz[p], n_tgt[p], &results[p], nullptr);
+            if (s == ICP_CUDA_ERROR || s == ICP_NCCL_ERROR) {
+                fatal.store(s);
+                break;
+            }
+            int expect = ICP_OK;
+            if (s != ICP_OK) worst.compare_exchange_strong(expect, s);
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int k = 1; k < want; ++k) threads.emplace_back(run, c->workers[(size_t)k]);
+    run(c->workers[0]);
+    for (auto& t : threads) t.join();
+    for (Ctx* w : c->workers) c->launches += w->launches, w->launches = 0;
+    if (fatal.load() != ICP_OK) {
+        c->err = "batch: a worker failed: " + c->workers[0]->err;
+        return fatal.load();
+    }
+    return worst.load();
 }
 
 }  // extern "C"

@@ -89,6 +89,10 @@ struct Ctx {
     IterRecord* h_rec = nullptr;  // pinned, device-mapped
     IterRecord* d_rec = nullptr;
 
+    // batch of small registrations: pool of worker handles (own stream each) on this device
+    std::vector<Ctx*> workers;
+    int opt_batch_workers = 8;
+
     // multi-GPU
     NcclApi* nccl = nullptr;
     void* comm = nullptr;

@@ -190,6 +190,29 @@ class Handle:
         self.check(st, ok=(0, 1, 2, 3))
         return _result_from_c(res, hist)
 
+    def register_batch(self, sources, targets) -> list:
+        """icp_register_batch: independent pairs (BASELINE.json config #5); every source array is updated in place."""
+        n = len(sources)
+        srcs = [_c3(a, writable=True) for a in sources]
+        tgts = [_c3(a) for a in targets]
+        p = _lib.IcpParams()
+        self.lib.icp_get_params(self.h, C.byref(p))
+        cap = p.max_iterations + 2
+        res = (_lib.IcpResult * n)()
+        hists = []
+        for k in range(n):
+            hst = (_lib.IcpIteration * cap)()
+            hists.append(hst)
+            res[k].history = C.cast(hst, C.POINTER(_lib.IcpIteration))
+            res[k].history_cap = cap
+        sp = (C.c_void_p * n)(*[a.ctypes.data for a in srcs])
+        tp = (C.c_void_p * n)(*[a.ctypes.data for a in tgts])
+        ns = (C.c_int64 * n)(*[len(a) for a in srcs])
+        nt = (C.c_int64 * n)(*[len(a) for a in tgts])
+        st = self.lib.icp_register_batch(self.h, n, sp, ns, tp, nt, res)
+        self.check(st, ok=(0, 1, 2, 3))
+        return [_result_from_c(res[k], hists[k]) for k in range(n)]
+
     def source_upload(self, source):
         src = _c3(source)
         self.check(self.lib.icp_source_upload(self.h, _ptr(src), len(src)))

@@ -380,3 +380,20 @@ def test_cpp_adapters_match_the_oracle(oracle, tmp_path):
     assert np.max(np.abs(np.array(out["finalT"]) - want.final_t)) <= REL_E2E
     moved = np.fromfile(sp + ".out").reshape(-1, 3)
     assert np.max(np.abs(moved - want.source_out)) <= 1e-9 * float(np.max(np.abs(moved)))
+
+
+def test_register_batch_equals_single_pair_runs_and_the_oracle(handle, oracle):
+    """BASELINE.json config #5 in small: independent pairs through icp_register_batch (worker streams)."""
+    pairs = [synth.small_pair(p, n=1500) for p in range(12)]
+    srcs = [s.copy() for s, _ in pairs]
+    handle.set_params(ICPParameters(maxIterations=40))
+    results = handle.register_batch(srcs, [t for _, t in pairs])
+    assert len(results) == 12
+    for k, ((s0, t), moved, r) in enumerate(zip(pairs, srcs, results)):
+        want = oracle.icp(s0, t, max_iterations=40)
+        _check_run(r, want, len(s0))
+        assert np.max(np.abs(moved - want.source_out)) <= 1e-9 * float(np.max(np.abs(want.source_out))), k
+    # same answers as one-at-a-time calls on the same handle
+    single = s0 = pairs[3][0].copy()
+    r1 = handle.register(single, pairs[3][1])
+    assert r1.totalIterations == results[3].totalIterations and np.array_equal(single, srcs[3])
