@@ -33,6 +33,11 @@ int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n);
 int unsort_results_launch(Ctx* c, const uint32_t* pos, const double* dist, const uint32_t* perm, int64_t n, int32_t* idx_out,
                           double* dist_out);
 int aos_to_soa_launch(Ctx* c, const double* xyz, int64_t n, double* sx, double* sy, double* sz);
+bool small_pair_eligible(int64_t n_src, int64_t n_tgt);
+int small_batch_run(Ctx* c, const std::vector<int32_t>& which, double* const* src_xyz, const int64_t* n_src,
+                    const double* const* tgt_xyz, const int64_t* n_tgt, std::vector<IterRecord>& recs, int rec_cap,
+                    std::vector<int>& n_rec, std::vector<int>& exit_code, std::vector<char>& flagged,
+                    const double*& moved_ptr, std::vector<long long>& src_off);
 
 // ------------------------------------------------------------------------------------------------
 // NCCL, resolved at run time so that the library shares the process's already-loaded libnccl.so.2
@@ -150,6 +155,100 @@ static int source_from_device_aos(Ctx* c, const double* d_xyz, int64_t n) {
     return aos_to_soa_launch(c, d_xyz, n, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p);
 }
 
+// Turns the per-iteration device records into the reference's result structures, applying the reference's own
+// bookkeeping (history, totalIterations, finalRMSE, which transform is "final", which exits write the source back).
+// Shared by the iteration loop below and by the batched small-problem path (batch.cu).
+struct RunAcc {
+    Ctx* c;
+    icp_result* out;
+    int variant, max_iterations;
+    long long n_global;
+    int n_hist = 0;
+    double last_rmse = 0.0, prev_error = 1e10;
+    double T_last[16], T_cum[16];
+    bool write_back = true;
+
+    RunAcc(Ctx* ctx, icp_result* o, int var, int max_it, long long ng) : c(ctx), out(o), variant(var), max_iterations(max_it), n_global(ng) {
+        identity16(T_last);
+        identity16(T_cum);
+        out->history_len = 0;
+        out->loop_iterations = 0;
+        out->status = ICP_OK;
+    }
+    void push(const icp_iteration& it, bool notify) {
+        if (out->history && n_hist < out->history_cap) out->history[n_hist] = it;
+        ++n_hist;
+        last_rmse = it.rmse;
+        if (notify && c->on_iteration) c->on_iteration(&it, c->user);                                       // icpengine.cpp:366
+        if (notify && c->on_progress) c->on_progress(it.iteration, max_iterations, it.rmse, c->user);       // :367
+    }
+    // returns true if the loop goes on
+    bool consume(const IterRecord& rec, int iter, float nn_ms, float iter_ms, bool notify) {
+        out->loop_iterations = iter + 1;
+        if (rec.problems > 0.0) log_msg(c, "warning: %.0f abnormal distance values", rec.problems);
+        log_msg(c, "  distance range: min=%.6f, max=%.6f", rec.dmin, rec.dmax);
+        log_msg(c, "  distance stats: mean=%.6f, std=%.6f, threshold=%.6f", rec.mean, rec.std_dev, rec.threshold);
+        log_msg(c, "  RMSE = %.6f (valid: %d/%lld, outliers removed: %d)", rec.rmse, rec.valid_points, n_global, rec.outlier_points);
+        std::memcpy(T_cum, rec.T_cum, sizeof T_cum);
+        std::memcpy(T_last, rec.T_last, sizeof T_last);
+        if (rec.exit_code == 0 || rec.exit_code == 3) prev_error = rec.rmse;
+        icp_iteration it;
+        std::memset(&it, 0, sizeof it);
+        it.iteration = iter + 1;
+        it.rmse = rec.rmse;
+        it.valid_points = rec.valid_points;
+        it.outlier_points = rec.outlier_points;
+        it.nn_ms = nn_ms;
+        it.iter_ms = iter_ms;
+        std::memcpy(it.transform, rec.T_cum, sizeof it.transform);
+        if (rec.exit_code == 1) {  // converged: icpengine.cpp:291-305 ; CLI :551-554
+            log_msg(c, "converged at iteration %d", iter + 1);
+            if (variant == ICP_VARIANT_ENGINE) {
+                it.has_angles = 0;  // the reference leaves the angle fields of this record unset (:294-303)
+                push(it, notify);
+            }
+            return false;
+        }
+        if (rec.exit_code == 2) {  // error grew: icpengine.cpp:311-314
+            log_msg(c, "warning: error increased, stopping");
+            return false;
+        }
+        if (rec.exit_code == 3) {  // < 3 inliers: icpengine.cpp:319-323 ; CLI :567-570 breaks and writes back
+            log_msg(c, "error: too few valid pairs to estimate a transform");
+            if (variant == ICP_VARIANT_ENGINE) {
+                out->status = ICP_TOO_FEW_INLIERS;
+                write_back = false;
+            }
+            return false;
+        }
+        it.has_angles = 1;
+        angles_of(rec.T_cum, &it.rotation_angle, &it.translation_distance);
+        push(it, notify);
+        return true;
+    }
+    void finish() {
+        std::memcpy(out->cumulative_T, T_cum, sizeof T_cum);
+        std::memcpy(out->last_T, T_last, sizeof T_last);
+        if (write_back) {
+            out->success = 1;
+            out->total_iterations = n_hist;                                  // icpengine.cpp:386
+            out->final_rmse = (variant == ICP_VARIANT_CLI) ? prev_error : (n_hist ? last_rmse : 0.0);
+            const double* F = (variant == ICP_VARIANT_CLI) ? T_last : T_cum;  // CLI: last incremental T (:616-621)
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) out->final_R[3 * i + j] = F[4 * i + j];
+                out->final_t[i] = F[4 * i + 3];
+            }
+        } else {
+            out->success = 0;
+            out->total_iterations = 0;
+            out->final_rmse = 0.0;
+            std::memset(out->final_R, 0, sizeof out->final_R);
+            std::memset(out->final_t, 0, sizeof out->final_t);
+        }
+        out->history_len = n_hist < (out->history ? out->history_cap : 0) ? n_hist : (out->history ? out->history_cap : 0);
+    }
+};
+
 // The iteration loop on the resident source/target.  n_global = N of the mean/variance.
 static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile int* stop_flag, bool* write_back) {
     const icp_params& P = c->params;
@@ -172,17 +271,10 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     hs.n_global = n_global;
     ICPB_CUDA(c, cudaMemcpyAsync(c->d_state, &hs, sizeof hs, cudaMemcpyHostToDevice, c->stream));
 
-    out->history_len = 0;
-    out->loop_iterations = 0;
-    out->status = ICP_OK;
+    RunAcc acc(c, out, variant, P.max_iterations, (long long)n_global);
     out->ms_nn_total = 0.f;
     out->ms_nn_first = 0.f;
     *write_back = true;
-    int n_hist = 0;
-    double last_rmse = 0.0, prev_error = 1e10;
-    double T_last[16], T_cum[16];
-    identity16(T_last);
-    identity16(T_cum);
 
     StatA* part_a = (StatA*)c->part_a.p + 64;  // first 64 entries are scratch of the build
     StatA* rank_a = (StatA*)c->gather_a.p;
@@ -199,7 +291,7 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         if (variant == ICP_VARIANT_ENGINE && stop_flag && *stop_flag) {  // icpengine.cpp:160-164
             log_msg(c, "registration stopped");
             out->status = ICP_CANCELLED;
-            *write_back = false;
+            acc.write_back = false;
             break;
         }
         log_msg(c, "iteration %d/%d ...", iter + 1, P.max_iterations);
@@ -244,81 +336,15 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         out->ms_nn_total += nn_ms;
         if (iter == 0) out->ms_nn_first = nn_ms;
         const IterRecord rec = *c->h_rec;
-        if (rec.problems > 0.0) log_msg(c, "warning: %.0f abnormal distance values", rec.problems);
-        log_msg(c, "  distance range: min=%.6f, max=%.6f", rec.dmin, rec.dmax);
-        log_msg(c, "  distance stats: mean=%.6f, std=%.6f, threshold=%.6f", rec.mean, rec.std_dev, rec.threshold);
-        log_msg(c, "  RMSE = %.6f (valid: %d/%lld, outliers removed: %d)", rec.rmse, rec.valid_points, (long long)n_global,
-                rec.outlier_points);
-        std::memcpy(T_cum, rec.T_cum, sizeof T_cum);
-        std::memcpy(T_last, rec.T_last, sizeof T_last);
-        if (rec.exit_code == 0 || rec.exit_code == 3) prev_error = rec.rmse;
-
-        icp_iteration it;
-        std::memset(&it, 0, sizeof it);
-        it.iteration = iter + 1;
-        it.rmse = rec.rmse;
-        it.valid_points = rec.valid_points;
-        it.outlier_points = rec.outlier_points;
-        it.nn_ms = nn_ms;
-        it.iter_ms = iter_ms;
-        std::memcpy(it.transform, rec.T_cum, sizeof it.transform);
-
-        if (rec.exit_code == 1) {  // converged: icpengine.cpp:291-305 ; CLI :551-554
-            log_msg(c, "converged at iteration %d", iter + 1);
-            if (variant == ICP_VARIANT_ENGINE) {
-                it.has_angles = 0;
-                if (out->history && n_hist < out->history_cap) out->history[n_hist] = it;
-                ++n_hist;
-                last_rmse = rec.rmse;
-                if (c->on_iteration) c->on_iteration(&it, c->user);
-                if (c->on_progress) c->on_progress(iter + 1, P.max_iterations, rec.rmse, c->user);
-            }
-            break;
-        }
-        if (rec.exit_code == 2) {  // error grew: icpengine.cpp:311-314
-            log_msg(c, "warning: error increased, stopping");
-            break;
-        }
-        if (rec.exit_code == 3) {  // < 3 inliers: icpengine.cpp:319-323 ; CLI :567-570 breaks and writes back
-            log_msg(c, "error: too few valid pairs to estimate a transform");
-            if (variant == ICP_VARIANT_ENGINE) {
-                out->status = ICP_TOO_FEW_INLIERS;
-                *write_back = false;
-            }
-            break;
-        }
-        it.has_angles = 1;
-        angles_of(rec.T_cum, &it.rotation_angle, &it.translation_distance);
-        if (out->history && n_hist < out->history_cap) out->history[n_hist] = it;
-        ++n_hist;
-        last_rmse = rec.rmse;
-        if (c->on_iteration) c->on_iteration(&it, c->user);                                     // icpengine.cpp:366
-        if (c->on_progress) c->on_progress(iter + 1, P.max_iterations, rec.rmse, c->user);     // :367
+        if (!acc.consume(rec, iter, nn_ms, iter_ms, true)) break;
     }
     ICPB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
 
-    out->history_len = std::min(n_hist, out->history ? out->history_cap : 0);
-    std::memcpy(out->cumulative_T, T_cum, sizeof T_cum);
-    std::memcpy(out->last_T, T_last, sizeof T_last);
     c->prev_valid = out->loop_iterations > 0 && c->opt_nn_mode >= 1;
-    if (*write_back) {
+    *write_back = acc.write_back;
+    if (acc.write_back)
         ICPB_TRY(apply_pending_launch(c, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p, n));  // the last T, if any
-        out->success = 1;
-        out->total_iterations = n_hist;                                  // icpengine.cpp:386
-        out->final_rmse = (variant == ICP_VARIANT_CLI) ? prev_error : (n_hist ? last_rmse : 0.0);
-        const double* F = (variant == ICP_VARIANT_CLI) ? T_last : T_cum;  // CLI: last incremental T (:616-621)
-        for (int i = 0; i < 3; ++i) {
-            for (int j = 0; j < 3; ++j) out->final_R[3 * i + j] = F[4 * i + j];
-            out->final_t[i] = F[4 * i + 3];
-        }
-    } else {
-        out->success = 0;
-        out->total_iterations = 0;
-        out->final_rmse = 0.0;
-        std::memset(out->final_R, 0, sizeof out->final_R);
-        std::memset(out->final_t, 0, sizeof out->final_t);
-    }
-    out->history_len = n_hist < (out->history ? out->history_cap : 0) ? n_hist : (out->history ? out->history_cap : 0);
+    acc.finish();
     ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
     {
         float ms = 0.f;
@@ -460,6 +486,8 @@ void icp_destroy(icp_handle h) {
     DevBuf* bufs[] = {&c->tgt_raw, &c->sx, &c->sy, &c->sz, &c->sperm, &c->pos, &c->dist, &c->mask, &c->part_a, &c->part_b,
                       &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io};
     for (DevBuf* b : bufs) devbuf_free(*b);
+    if (c->pin_a.p) cudaFreeHost(c->pin_a.p);
+    if (c->pin_b.p) cudaFreeHost(c->pin_b.p);
     if (c->d_state) cudaFree(c->d_state);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->h_rec) cudaFreeHost(c->h_rec);
@@ -515,6 +543,7 @@ int icp_set_option(icp_handle h, const char* key, double value) {
         c->prev_valid = false;
     }
     else if (!strcmp(key, "count")) c->opt_count = value != 0.0;
+    else if (!strcmp(key, "batch_small")) c->opt_batch_small = value != 0.0;
     else if (!strcmp(key, "batch_workers")) c->opt_batch_workers = std::min(std::max((int)value, 1), 64);
     else if (!strcmp(key, "base_occupancy")) c->opt_base_occupancy = std::max(value, 1.0);
     else if (!strcmp(key, "grid_levels")) c->opt_grid_levels = std::min(std::max((int)value, 1), 4);
@@ -919,7 +948,7 @@ int icp_register_batch(icp_handle h, int32_t n_pairs, double* const* src_xyz, co
     Ctx* c = (Ctx*)h;
     if (!c || n_pairs < 0 || (n_pairs > 0 && (!src_xyz || !n_src || !tgt_xyz || !n_tgt || !results))) return ICP_INVALID_ARGUMENT;
     if (n_pairs == 0) return ICP_OK;
-    const int want = std::max(1, std::min(std::min(c->opt_batch_workers, (int)n_pairs), 64));
+    auto ensure_workers = [&](int want) -> int {
     while ((int)c->workers.size() < want) {
         icp_handle w = nullptr;
         if (icp_create(&w, c->device) != ICP_OK) {
@@ -928,16 +957,92 @@ int icp_register_batch(icp_handle h, int32_t n_pairs, double* const* src_xyz, co
         }
         c->workers.push_back((Ctx*)w);
     }
-    std::atomic<int32_t> next{0};
+    return ICP_OK;
+    };
+    // ---- small pairs: one thread block each, all in one launch (batch.cu) ---------------------------------------------
+    std::vector<int32_t> todo;  // pairs left for the general path
     std::atomic<int> fatal{ICP_OK}, worst{ICP_OK};
+    {
+        std::vector<int32_t> small;
+        for (int32_t p = 0; p < n_pairs; ++p) {
+            if (c->opt_batch_small && src_xyz[p] && tgt_xyz[p] && small_pair_eligible(n_src[p], n_tgt[p]) && !c->on_iteration &&
+                !c->on_progress && !c->on_log)
+                small.push_back(p);
+            else
+                todo.push_back(p);
+        }
+        if (!small.empty()) {
+            // chunks of a few waves of blocks, spread over up to three lanes (this handle + two workers, one host
+            // thread and one stream each): while one lane's kernel runs, the others pack / copy / unpack
+            const int rec_cap = c->params.max_iterations + 1;
+            const int chunk = std::max(c->sm_count * 2, 64);
+            const int n_chunks = ((int)small.size() + chunk - 1) / chunk;
+            const int lanes = std::min(3, n_chunks);
+            if (lanes > 1) ICPB_TRY(ensure_workers(lanes - 1));
+            std::vector<std::vector<int32_t>> redo((size_t)lanes);
+            std::atomic<int> next_chunk{0};
+            auto lane_fn = [&](int lane) {
+                Ctx* w = (lane == 0) ? c : c->workers[(size_t)lane - 1];
+                cudaSetDevice(w->device);
+                if (w != c) w->params = c->params;
+                std::vector<IterRecord> recs;
+                std::vector<int> n_rec, exit_code;
+                std::vector<char> flagged;
+                std::vector<long long> src_off;
+                for (;;) {
+                    const int ci = next_chunk.fetch_add(1);
+                    if (ci >= n_chunks || fatal.load() != ICP_OK) break;
+                    const std::vector<int32_t> part(small.begin() + (size_t)ci * chunk,
+                                                    small.begin() + std::min(small.size(), (size_t)(ci + 1) * chunk));
+                    const double* moved = nullptr;
+                    const int s = small_batch_run(w, part, src_xyz, n_src, tgt_xyz, n_tgt, recs, rec_cap, n_rec, exit_code, flagged, moved,
+                                                  src_off);
+                    if (s != ICP_OK) {
+                        if (w != c) c->err = w->err;
+                        fatal.store(s);
+                        break;
+                    }
+                    for (size_t k = 0; k < part.size(); ++k) {
+                        const int32_t p = part[k];
+                        if (flagged[k]) {
+                            redo[(size_t)lane].push_back(p);
+                            continue;
+                        }
+                        init_result(&results[p]);
+                        RunAcc acc(w, &results[p], c->params.variant, c->params.max_iterations, (long long)n_src[p]);
+                        for (int r = 0; r < n_rec[k]; ++r)
+                            if (!acc.consume(recs[k * (size_t)rec_cap + (size_t)r], r, 0.f, 0.f, false)) break;
+                        acc.finish();
+                        if (acc.write_back)  // icpengine.cpp:371-375
+                            std::memcpy(src_xyz[p], moved + 3 * src_off[k], (size_t)n_src[p] * 3 * sizeof(double));
+                        int expect = ICP_OK;
+                        if (results[p].status != ICP_OK) worst.compare_exchange_strong(expect, results[p].status);
+                    }
+                }
+            };
+            std::vector<std::thread> lane_threads;
+            for (int l = 1; l < lanes; ++l) lane_threads.emplace_back(lane_fn, l);
+            lane_fn(0);
+            for (auto& t : lane_threads) t.join();
+            if (fatal.load() != ICP_OK) return fatal.load();
+            for (auto& r : redo) todo.insert(todo.end(), r.begin(), r.end());
+        }
+    }
+    if (todo.empty()) return worst.load();
+    const int n_todo = (int)todo.size();
+    const int want = std::max(1, std::min(std::min(c->opt_batch_workers, n_todo), 64));
+    ICPB_TRY(ensure_workers(want));
+    std::atomic<int32_t> next{0};
+
     auto run = [&](Ctx* w) {
         cudaSetDevice(w->device);
         w->params = c->params;
         w->opt_nn_mode = c->opt_nn_mode;
         w->opt_order_queries = c->opt_order_queries;
         for (;;) {
-            const int32_t p = next.fetch_add(1);
-            if (p >= n_pairs || fatal.load() != ICP_OK) break;
+            const int32_t q = next.fetch_add(1);
+            if (q >= n_todo || fatal.load() != ICP_OK) break;
+            const int32_t p = todo[(size_t)q];
             const int s = register_impl(w, src_xyz[p], n_src[p], n_src[p], tgt_xyz[p], n_tgt[p], &results[p], nullptr);
             if (s == ICP_CUDA_ERROR || s == ICP_NCCL_ERROR) {
                 fatal.store(s);

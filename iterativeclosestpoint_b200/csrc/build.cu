@@ -30,6 +30,17 @@ int devbuf_reserve(Ctx* c, DevBuf& b, size_t bytes) {
     return ICP_OK;
 }
 
+int pinned_reserve(Ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return ICP_OK;
+    if (b.p) ICPB_CUDA(c, cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    ICPB_CUDA(c, cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
+    b.cap = want;
+    return ICP_OK;
+}
+
 void devbuf_free(DevBuf& b) {
     if (b.p) cudaFree(b.p);
     b.p = nullptr;

@@ -45,6 +45,7 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[12] = {};
+    DevBuf pin_a, pin_b;       // pinned host staging (grow-only), batch path
     std::string err;
     icp_params params;
     icp_iteration_cb on_iteration = nullptr;
@@ -92,6 +93,7 @@ struct Ctx {
     // batch of small registrations: pool of worker handles (own stream each) on this device
     std::vector<Ctx*> workers;
     int opt_batch_workers = 8;
+    bool opt_batch_small = true;     // pairs of <= 2048 / 4096 points go through the one-block kernel (batch.cu)
 
     // multi-GPU
     NcclApi* nccl = nullptr;
@@ -117,6 +119,7 @@ struct Ctx {
     } while (0)
 
 int devbuf_reserve(Ctx* c, DevBuf& b, size_t bytes);
+int pinned_reserve(Ctx* c, DevBuf& b, size_t bytes);
 void devbuf_free(DevBuf& b);
 
 // build.cu

@@ -209,7 +209,10 @@ class Handle:
         tp = (C.c_void_p * n)(*[a.ctypes.data for a in tgts])
         ns = (C.c_int64 * n)(*[len(a) for a in srcs])
         nt = (C.c_int64 * n)(*[len(a) for a in tgts])
+        import time as _time
+        t0 = _time.perf_counter()
         st = self.lib.icp_register_batch(self.h, n, sp, ns, tp, nt, res)
+        self.last_batch_seconds = _time.perf_counter() - t0   # the C call alone (result unpacking below is Python overhead)
         self.check(st, ok=(0, 1, 2, 3))
         return [_result_from_c(res[k], hists[k]) for k in range(n)]
 

@@ -382,18 +382,36 @@ def test_cpp_adapters_match_the_oracle(oracle, tmp_path):
     assert np.max(np.abs(moved - want.source_out)) <= 1e-9 * float(np.max(np.abs(moved)))
 
 
-def test_register_batch_equals_single_pair_runs_and_the_oracle(handle, oracle):
-    """BASELINE.json config #5 in small: independent pairs through icp_register_batch (worker streams)."""
-    pairs = [synth.small_pair(p, n=1500) for p in range(12)]
+@pytest.mark.parametrize("small", [1, 0], ids=["one_block_kernel", "worker_streams"])
+def test_register_batch_matches_the_oracle(handle, oracle, small):
+    """BASELINE.json config #5 in small: independent pairs through icp_register_batch -- the one-block-per-pair kernel
+    (batch.cu) and the worker-stream path, plus pairs the small kernel must hand back (duplicate target points = exact
+    ties, a cloud too large for it, an empty cloud)."""
+    pairs = [synth.small_pair(p, n=1500) for p in range(10)]
+    dup_s, dup_t = synth.small_pair(100, n=800)
+    dup_t = np.ascontiguousarray(np.concatenate([dup_t, dup_t[:50]]))     # exact duplicates -> ties -> literal path
+    big_s, big_t = synth.make_pair(6000, 2, "near")                        # above the one-block limits
+    pairs += [(dup_s, dup_t), (big_s, big_t)]
     srcs = [s.copy() for s, _ in pairs]
+    handle.set_option("batch_small", small)
     handle.set_params(ICPParameters(maxIterations=40))
     results = handle.register_batch(srcs, [t for _, t in pairs])
-    assert len(results) == 12
+    assert len(results) == len(pairs)
     for k, ((s0, t), moved, r) in enumerate(zip(pairs, srcs, results)):
         want = oracle.icp(s0, t, max_iterations=40)
         _check_run(r, want, len(s0))
         assert np.max(np.abs(moved - want.source_out)) <= 1e-9 * float(np.max(np.abs(want.source_out))), k
-    # same answers as one-at-a-time calls on the same handle
-    single = s0 = pairs[3][0].copy()
+    # one-at-a-time call on the same handle: same run
+    single = pairs[3][0].copy()
     r1 = handle.register(single, pairs[3][1])
-    assert r1.totalIterations == results[3].totalIterations and np.array_equal(single, srcs[3])
+    assert r1.totalIterations == results[3].totalIterations
+    assert np.max(np.abs(single - srcs[3])) <= 1e-12 * float(np.max(np.abs(single)))
+
+
+def test_register_batch_failure_exits(handle, oracle):
+    tiny_s = np.array([[0.0, 0, 0], [1.0, 0, 0]]); tiny_t = np.array([[0, 0, 0.1], [1, 0, 0.1], [0, 1, 0.1]], dtype=np.float64)
+    ok_s, ok_t = synth.small_pair(7, n=600)
+    srcs = [tiny_s.copy(), ok_s.copy()]
+    res = handle.register_batch(srcs, [tiny_t, ok_t])
+    assert res[0].status == 3 and not res[0].success and np.array_equal(srcs[0], tiny_s)   # icpengine.cpp:319-323
+    assert res[1].success and res[1].totalIterations == oracle.icp(ok_s, ok_t).total_iterations
