@@ -391,16 +391,25 @@ static int register_impl(Ctx* c, double* src_xyz, int64_t n_src, int64_t n_src_g
     ICPB_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
     ICPB_TRY(upload(c, c->tgt_raw, tgt_xyz, n_tgt));
     c->n_tgt = n_tgt;
+    // the source goes up on a second stream so that (from pinned memory) its copy overlaps the target's tree build
     DevBuf& src_stage = c->scratch_src;
-    if (n_src > 0) ICPB_TRY(upload(c, src_stage, src_xyz, n_src));
     ICPB_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+    if (n_src > 0) {
+        ICPB_TRY(devbuf_reserve(c, src_stage, (size_t)n_src * 3 * sizeof(double)));
+        ICPB_CUDA(c, cudaStreamWaitEvent(c->stream2, c->ev[5], 0));  // after the target copy: one copy engine direction, FIFO
+        ICPB_CUDA(c, cudaMemcpyAsync(src_stage.p, src_xyz, (size_t)n_src * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream2));
+        ICPB_CUDA(c, cudaEventRecord(c->ev_src, c->stream2));
+    }
     log_msg(c, "building the target octree ...");
     ICPB_TRY(octree_build_device(c, (const double*)c->tgt_raw.p, n_tgt, leaf, depth));
     log_msg(c, "octree built: %lld nodes, %lld leaves, depth %d", (long long)c->tree.n_nodes, (long long)c->tree.n_leaves,
             c->tree.depth);
     c->src_identity_perm = false;
     c->n_src = n_src;
-    if (n_src > 0) ICPB_TRY(source_from_device_aos(c, (const double*)src_stage.p, n_src));
+    if (n_src > 0) {
+        ICPB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_src, 0));
+        ICPB_TRY(source_from_device_aos(c, (const double*)src_stage.p, n_src));
+    }
     ICPB_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
 
     bool write_back = true;
@@ -460,6 +469,8 @@ int icp_create(icp_handle* out, int device_id) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    if (cudaEventCreateWithFlags(&c->ev_src, cudaEventDisableTiming) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     for (auto& e : c->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaMalloc(&c->d_state, sizeof(LoopState)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
@@ -493,6 +504,8 @@ void icp_destroy(icp_handle h) {
     if (c->h_rec) cudaFreeHost(c->h_rec);
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
+    if (c->ev_src) cudaEventDestroy(c->ev_src);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c->nccl;
     delete c;

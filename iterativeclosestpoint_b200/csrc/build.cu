@@ -190,12 +190,18 @@ __global__ void __launch_bounds__(BBOX_THREADS) bbox_partial_kernel(const double
     }
 }
 
-__global__ void bbox_finish_kernel(const double* __restrict__ part, int n_part, const double* __restrict__ xyz,
-                                   double* __restrict__ root /* lo[3], hi[3] */) {
-    const int a = threadIdx.x;
-    if (a >= 6) return;
-    double v = part[a];
-    for (int k = 1; k < n_part; ++k) v = (a < 3) ? fmin(v, part[(int64_t)k * 6 + a]) : fmax(v, part[(int64_t)k * 6 + a]);
+__global__ void __launch_bounds__(192) bbox_finish_kernel(const double* __restrict__ part, int n_part, const double* __restrict__ xyz,
+                                                          double* __restrict__ root /* lo[3], hi[3] */) {
+    // warp a (0..5) reduces component a of the block partials; min/max are order-independent
+    const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double v = (a < 3) ? DBL_MAX : -DBL_MAX;
+    for (int k = lane; k < n_part; k += 32) v = (a < 3) ? fmin(v, part[(int64_t)k * 6 + a]) : fmax(v, part[(int64_t)k * 6 + a]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = (a < 3) ? fmin(v, w) : fmax(v, w);
+    }
+    if (lane != 0) return;
     const double p0 = xyz[a % 3];
     if (p0 != p0) v = p0;  // pts[0] seeds the scan (octree.cpp:47-49): a NaN there sticks
     const double eps = 0.001;
@@ -547,7 +553,7 @@ static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, i
     double* d_part = (double*)c->scratch0.p;
     double* d_root = d_part + (size_t)bb_blocks * 6;
     bbox_partial_kernel<<<bb_blocks, BBOX_THREADS, 0, s>>>(d_xyz, m, d_part);
-    bbox_finish_kernel<<<1, 32, 0, s>>>(d_part, bb_blocks, d_xyz, d_root);
+    bbox_finish_kernel<<<1, 192, 0, s>>>(d_part, bb_blocks, d_xyz, d_root);
     c->launches += 2;
     if (cubic) {
         cube_root_kernel<<<1, 32, 0, s>>>(d_root);
@@ -654,13 +660,22 @@ static int build_inv_perm_of(Ctx* c, DeviceOctree& t) {
 // instead of walking down from the root or up from a previous leaf.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) leaf_depth_hist_kernel(const Node* __restrict__ nodes, int64_t n_nodes,
-                                                              unsigned long long* __restrict__ hist /* [32] */) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    const uint32_t meta = nodes[i].meta;
-    if ((meta & 0xFFu) == 0u) atomicAdd(&hist[(meta >> 8) & 0x1Fu], (unsigned long long)nodes[i].npts);
-    atomicAdd(&hist[32 + ((meta >> 8) & 0x1Fu)], 1ull);                                 // nodes per depth
-    atomicAdd(&hist[64 + ((meta >> 8) & 0x1Fu)], (unsigned long long)nodes[i].npts);    // points that reach that depth
+                                                              unsigned long long* __restrict__ hist /* [96] */) {
+    // [0,32): points in leaves per depth; [32,64): nodes per depth; [64,96): points that reach each depth.
+    // Privatised in shared memory: three same-address global atomics per node would serialise the whole kernel.
+    __shared__ unsigned long long sh[96];
+    if (threadIdx.x < 96) sh[threadIdx.x] = 0ull;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t meta = nodes[i].meta;
+        const uint32_t npts = nodes[i].npts;
+        const uint32_t d = (meta >> 8) & 0x1Fu;
+        if ((meta & 0xFFu) == 0u) atomicAdd(&sh[d], (unsigned long long)npts);
+        atomicAdd(&sh[32 + d], 1ull);
+        atomicAdd(&sh[64 + d], (unsigned long long)npts);
+    }
+    __syncthreads();
+    if (threadIdx.x < 96 && sh[threadIdx.x] != 0ull) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(128) grid_fill_kernel(const Node* __restrict__ nodes, const uint64_t* __restrict__ cell,
@@ -697,7 +712,7 @@ static int build_grid(Ctx* c, DeviceOctree& t) {
     ICPB_TRY(devbuf_reserve(c, c->scratch0, 96 * sizeof(unsigned long long)));
     unsigned long long* d_hist = (unsigned long long*)c->scratch0.p;
     ICPB_CUDA(c, cudaMemsetAsync(d_hist, 0, 96 * sizeof(unsigned long long), s));
-    leaf_depth_hist_kernel<<<(int)((t.n_nodes + 255) / 256), 256, 0, s>>>(t.nodes, t.n_nodes, d_hist);
+    leaf_depth_hist_kernel<<<(int)std::min<int64_t>((t.n_nodes + 255) / 256, (int64_t)c->sm_count * 8), 256, 0, s>>>(t.nodes, t.n_nodes, d_hist);
     c->launches++;
     unsigned long long hist[96];
     ICPB_CUDA(c, cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, s));
@@ -792,6 +807,11 @@ int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int
 // nodes.  Queries are ordered by a 3x21-bit Morton code of their own bounding box (this is only a
 // permutation for locality -- any order gives the same per-query answer).
 // ------------------------------------------------------------------------------------------------
+// 13 bits per axis (8192^3 cells: centimetres on a 100 m tile, ~0.4 m on a 3 km one) order the queries finely enough for
+// neighbouring threads to share cells, and keep the sort at 5 radix passes instead of 8.
+constexpr int QKEY_BITS = 13;
+constexpr uint32_t QKEY_MAX = (1u << QKEY_BITS) - 1u;
+
 __global__ void __launch_bounds__(256) query_keys_kernel(const double* __restrict__ xyz, int64_t n,
                                                          const double* __restrict__ box, uint64_t* __restrict__ keys,
                                                          uint32_t* __restrict__ idx) {
@@ -801,17 +821,17 @@ __global__ void __launch_bounds__(256) query_keys_kernel(const double* __restric
     // compact, roughly cubic clump (a per-axis scale would slice 2.5-D scenes into thin height slabs whose tiles
     // follow contour lines).
     const double ext = fmax(fmax(box[3] - box[0], box[4] - box[1]), box[5] - box[2]);
-    const double inv = ext > 0.0 ? 2097151.0 / ext : 0.0;
+    const double inv = ext > 0.0 ? (double)QKEY_MAX / ext : 0.0;
     uint64_t key = 0;
     uint32_t q[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         double f = (xyz[3 * i + a] - box[a]) * inv;
         if (!(f > 0.0)) f = 0.0;  // also catches NaN
-        if (f > 2097151.0) f = 2097151.0;
+        if (f > (double)QKEY_MAX) f = (double)QKEY_MAX;
         q[a] = (uint32_t)f;
     }
-    for (int b = 20; b >= 0; --b)
+    for (int b = QKEY_BITS - 1; b >= 0; --b)
         key = (key << 3) | (((q[0] >> b) & 1u)) | (((q[1] >> b) & 1u) << 1) | (((q[2] >> b) & 1u) << 2);
     keys[i] = key;
     idx[i] = (uint32_t)i;
@@ -836,7 +856,7 @@ int order_queries(Ctx* c, const double* d_q, int64_t n, double* sx, double* sy, 
     double* d_part = (double*)c->scratch0.p;
     double* d_box = d_part + (size_t)bb_blocks * 6;
     bbox_partial_kernel<<<bb_blocks, BBOX_THREADS, 0, s>>>(d_q, n, d_part);
-    bbox_finish_kernel<<<1, 32, 0, s>>>(d_part, bb_blocks, d_q, d_box);
+    bbox_finish_kernel<<<1, 192, 0, s>>>(d_part, bb_blocks, d_q, d_box);
     ICPB_TRY(devbuf_reserve(c, c->scratch1, (size_t)n * (2 * sizeof(uint64_t) + 2 * sizeof(uint32_t)) + 1024));
     uint64_t* keys = (uint64_t*)c->scratch1.p;
     uint64_t* keys_alt = keys + n;
@@ -845,7 +865,7 @@ int order_queries(Ctx* c, const double* d_q, int64_t n, double* sx, double* sy, 
     const int kb = (int)((n + 255) / 256);
     query_keys_kernel<<<kb, 256, 0, s>>>(d_q, n, d_box, keys, idx);
     c->launches += 3;
-    ICPB_TRY(radix_sort_pairs(c, keys, keys_alt, idx, idx_alt, n, 63));
+    ICPB_TRY(radix_sort_pairs(c, keys, keys_alt, idx, idx_alt, n, 3 * QKEY_BITS));
     gather_soa_kernel<<<kb, 256, 0, s>>>(d_q, idx, n, sx, sy, sz, perm);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());

@@ -44,6 +44,8 @@ struct NcclApi;  // comm.cu
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // source upload, overlapped with the target's tree build
+    cudaEvent_t ev_src = nullptr;
     cudaEvent_t ev[12] = {};
     DevBuf pin_a, pin_b;       // pinned host staging (grow-only), batch path
     std::string err;
@@ -58,7 +60,7 @@ struct Ctx {
     DeviceOctree tree;  // the reference's octree (structure parity, literal traversal)
     DeviceOctree fast;  // isotropic search tree over the same points; match positions index ITS point order
     int opt_search_leaf = 4;         // leaf capacity of the search tree
-    int opt_search_depth = 21;       // depth cap of the search tree
+    int opt_search_depth = 16;       // depth cap of the search tree
     int opt_terminal_pts = 16;       // tile kernel stages subtrees up to this size whole
     int opt_grid_shift = 0;          // entry grid level relative to the median leaf depth
     long long opt_grid_max_cells = 1ll << 28;  // entries (8 B each) over the whole pyramid
