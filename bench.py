@@ -231,17 +231,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from iterativeclosestpoint_b200 import sharding
+
     src, tgt = make_workload(M, args.regime)
-    lo = (M * rank) // world
-    hi = (M * (rank + 1)) // world
+    lo, hi = sharding.shard_range(M, rank, world)
     shard = np.ascontiguousarray(src[lo:hi])
 
     h = Handle(local_rank)
     h.set_option("nn_mode", args.nn_mode)
     if world > 1:
-        uid = [h.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        h.comm_init(rank, world, uid[0])
+        sharding.init_sharded(h, dist, rank, world)  # rank 0's NCCL id -> everyone -> icp_comm_init
 
     # ---- device-resident figure ---------------------------------------------------------------------------
     h.octree_build(tgt, 10, 20)
@@ -321,6 +320,9 @@ def main():
                        if M >= 4_000_000 else "inputs smaller than L2; no flush", "parallelism": f"source sharded x{world}, octree replicated",
                        "octree": {"nodes": int(info.n_nodes), "leaves": int(info.n_leaves), "depth": int(info.depth),
                                   "build_ms": float(info.build_ms)},
+                       "search": {"nodes": int(info.search_nodes), "depth": int(info.search_depth),
+                                  "grid_levels": [int(info.grid_base_level), int(info.grid_fine_level)],
+                                  "grid_base_cell_m": float(info.grid_base_cell), "grid_bytes": int(info.grid_bytes)},
                        "nn_mode": args.nn_mode},
             "icp_iterations_per_s": iters / (loop_ms * 1e-3),
             "nn_kernel_queries_per_s": M / (nn_launch_ms * 1e-3) if world == 1 else n_local * world / (nn_launch_ms * 1e-3),

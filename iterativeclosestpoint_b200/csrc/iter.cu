@@ -227,7 +227,7 @@ __device__ __forceinline__ void sum_partials_fixed(const double* part, int n_par
 // partials -- identical arithmetic in every block and on every rank -- then owns block-strided tiles (fixed
 // geometry => fixed summation order).  The last block to finish sums the block partials in index order into this
 // rank's slot and, on a single-rank run, goes straight on to the solve.
-__global__ void __launch_bounds__(RED_THREADS, 3) stage_b_kernel(const double* __restrict__ sx, const double* __restrict__ sy,
+__global__ void __launch_bounds__(RED_THREADS, 2) stage_b_kernel(const double* __restrict__ sx, const double* __restrict__ sy,
                                                               const double* __restrict__ sz, const uint32_t* __restrict__ pos,
                                                               const double* __restrict__ dist, int64_t n,
                                                               const TPoint* __restrict__ pts, LoopState* __restrict__ st,
@@ -254,17 +254,37 @@ __global__ void __launch_bounds__(RED_THREADS, 3) stage_b_kernel(const double* _
     }
     AccB acc;
     accb_zero(acc);
-    for (int64_t base = (int64_t)blockIdx.x * RED_THREADS; base < n; base += (int64_t)gridDim.x * RED_THREADS) {
-        const int64_t i = base + threadIdx.x;
-        if (i >= n) break;
-        const double d = dist[i];
-        const uint32_t p = pos[i];
-        const bool ok = (d <= thr) && (p != 0xFFFFFFFFu);  // icpengine.cpp:264-268 (NaN => outlier)
-        if (mask_out) mask_out[i] = ok ? 1 : 0;
-        if (ok) {
-            const TPoint t = pts[p];
-            accb_add_pair(acc, d, sx[i], sy[i], sz[i], t.x, t.y, t.z, pa, pb);
+    // four tiles per trip: the four (distance, match) loads and then the four gathers are in flight together; the order
+    // in which a thread adds its queries is still fixed by the launch geometry alone
+    constexpr int UNR = 4;
+    const int64_t stride = (int64_t)gridDim.x * RED_THREADS;
+    for (int64_t base = (int64_t)blockIdx.x * RED_THREADS; base < n; base += stride * UNR) {
+        double d[UNR];
+        uint32_t p[UNR];
+        bool ok[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t i = base + u * stride + threadIdx.x;
+            d[u] = (i < n) ? dist[i] : 0.0;
+            p[u] = (i < n) ? pos[i] : 0xFFFFFFFFu;
         }
+        double ax[UNR], ay[UNR], az[UNR];
+        TPoint t[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t i = base + u * stride + threadIdx.x;
+            ok[u] = (i < n) && (d[u] <= thr) && (p[u] != 0xFFFFFFFFu);  // icpengine.cpp:264-268 (NaN => outlier)
+            if (mask_out && i < n) mask_out[i] = ok[u] ? 1 : 0;
+            if (ok[u]) {
+                t[u] = pts[p[u]];
+                ax[u] = sx[i];
+                ay[u] = sy[i];
+                az[u] = sz[i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+            if (ok[u]) accb_add_pair(acc, d[u], ax[u], ay[u], az[u], t[u].x, t[u].y, t[u].z, pa, pb);
     }
     accb_block_reduce(acc, part + (int64_t)blockIdx.x * STATB_DOUBLES);
     __syncthreads();

