@@ -476,11 +476,12 @@ int icp_create(icp_handle* out, int device_id) {
     if (cudaMalloc(&c->d_state, sizeof(LoopState)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long));
+    if (cudaMalloc(&c->d_work_count, sizeof(unsigned int)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaHostAlloc(&c->h_rec, sizeof(IterRecord), cudaHostAllocMapped) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaHostGetDevicePointer(&c->d_rec, c->h_rec, 0) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (getenv("ICP_B200_DEBUG_COUNTERS")) c->opt_count = true;
     const char* m = getenv("ICP_B200_NN_MODE");
-    if (m) c->opt_nn_mode = std::min(std::max(atoi(m), 0), 3);
+    if (m) c->opt_nn_mode = std::min(std::max(atoi(m), 0), 4);
     *out = (icp_handle)c;
     return ICP_OK;
 }
@@ -501,6 +502,7 @@ void icp_destroy(icp_handle h) {
     if (c->pin_b.p) cudaFreeHost(c->pin_b.p);
     if (c->d_state) cudaFree(c->d_state);
     if (c->d_counters) cudaFree(c->d_counters);
+    if (c->d_work_count) cudaFree(c->d_work_count);
     if (c->h_rec) cudaFreeHost(c->h_rec);
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
@@ -552,7 +554,7 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     Ctx* c = (Ctx*)h;
     if (!c || !key) return ICP_INVALID_ARGUMENT;
     if (!strcmp(key, "nn_mode")) {
-        c->opt_nn_mode = value < 0.5 ? 0 : (value < 1.5 ? 1 : (value < 2.5 ? 2 : 3));
+        c->opt_nn_mode = value < 0.5 ? 0 : (value < 1.5 ? 1 : (value < 2.5 ? 2 : (value < 3.5 ? 3 : 4)));
         c->prev_valid = false;
     }
     else if (!strcmp(key, "count")) c->opt_count = value != 0.0;

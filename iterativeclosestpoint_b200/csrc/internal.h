@@ -67,7 +67,8 @@ struct Ctx {
     int opt_grid_levels = 3;         // pyramid height (base level + finer ones)
     double opt_base_occupancy = 4.0; // mean points per occupied cell the base level must still have
     int opt_range_max = 64;          // inner cells up to this many points are entered as plain point ranges
-    int opt_walk_bias = -2;          // cell walk: levels finer (+) or coarser (-) than 'cell >= ball box'
+    int opt_walk_bias = -100;        // cell walk: levels finer (+) or coarser (-) than 'cell >= ball box'; -100 = per mode
+                                     // (measured best: -2 for the per-thread walk, 0 for the balanced one)
     int opt_walk_max_cells = 27;     // cell walk gives way to the climbing search beyond this many cells
     DevBuf tgt_raw;  // original-order target AoS (kept for the stage API)
     int64_t n_tgt = 0;
@@ -83,12 +84,13 @@ struct Ctx {
     bool prev_valid = false;         // pos / node_io hold last run's matches of the resident source against the current tree
     float last_build_ms = 0.f;
     // tuning knobs (icp_set_option)
-    int opt_nn_mode = 3;             // 0: literal traversal from the root; 1: per-thread fast path; 2: warp tiles
+    int opt_nn_mode = 4;             // 0: literal traversal from the root; 1: climb; 2: warp tiles; 3: cell walk; 4: balanced cell walk
     bool opt_order_queries = true;   // Morton-order the source for traversal coherence
     bool opt_write_mask = false;     // keep the per-point inlier mask of the last iteration
     bool opt_count = false;          // maintain the NN path counters (same-address atomics: profiling / tests only)
     LoopState* d_state = nullptr;
     unsigned long long* d_counters = nullptr;  // see NNArgs::counters (4 entries)
+    unsigned int* d_work_count = nullptr;      // mode 4: length of the work list (kept in node_io) for the per-thread kernel
     IterRecord* h_rec = nullptr;  // pinned, device-mapped
     IterRecord* d_rec = nullptr;
 

@@ -20,6 +20,7 @@
 //   (every box outside that node is farther than the bound).  Any point it did not look at has
 //   s > best (1 + 2^-39).  If second <= best (1 + 2^-40) (exact ties, duplicates, 1-ulp near ties) the query
 //   is re-run through `dfs_literal`; otherwise the unique minimum is the reference's answer.
+#include <algorithm>
 #include "nn_common.cuh"
 
 namespace icpb {
@@ -43,62 +44,80 @@ __device__ __forceinline__ StatA warp_merge(StatA v) {
     return v;
 }
 
+// One query through the per-thread search.  `moved`: the coordinates in A.sx are final (no pending transform).
+__device__ __forceinline__ void nn_one_query(const NNArgs& A, const long long i, const bool moved, uint2* stk, StatA& st,
+                                             bool& fell_back) {
+    double qx = A.sx[i], qy = A.sy[i], qz = A.sz[i];
+    if (!moved && A.apply_pending && A.state->have_T) {
+        apply_T_point(A.state->T_pending, qx, qy, qz);
+        A.ox[i] = qx;
+        A.oy[i] = qy;
+        A.oz[i] = qz;
+    }
+    const bool finite_q = isfinite(qx) && isfinite(qy) && isfinite(qz);
+    uint32_t pp = NONE, pn = NONE;
+    if (A.mode == 1 && A.prev_pos && A.node_io) {
+        pp = A.prev_pos[i];
+        pn = A.node_io[i];
+    } else if (A.mode == 3 && A.prev_pos) {
+        pp = A.prev_pos[i];
+    }
+    uint32_t result_node = NONE;
+    double best_s;
+    const uint32_t result = per_thread_query<NN_THREADS>(A, qx, qy, qz, finite_q, pp, pn, ICPB_INF, stk, result_node, fell_back,
+                                                         false, &best_s);
+    // findNearest returns index 0 when nothing was accepted (best_idx = 0 initially, octree.cpp:179)
+    const uint32_t pos = (result == NONE) ? A.pos_of_idx0 : result;
+    // computeDistance(p_src, p_tgt) (icpengine.cpp:68-74) = sqrt(dx*dx + dy*dy + dz*dz) with d = src - tgt; the search
+    // evaluated the same sum with d = tgt - src, whose squares are the same doubles, so its value is reused.
+    double d;
+    if (best_s >= 0.0) {
+        d = dsqrt(best_s);
+    } else {
+        double px, py, pz;
+        uint32_t pidx;
+        load_point(A.pts, pos, px, py, pz, pidx);
+        d = dsqrt(sumsq3(dsub(qx, px), dsub(qy, py), dsub(qz, pz)));
+    }
+    A.pos_out[i] = pos;
+    if (A.node_io && !A.worklist) A.node_io[i] = result_node;
+    A.dist_out[i] = d;
+    st.n = 1.0;
+    st.mean = d;
+    if (isfinite(d)) {
+        st.dmin = d;
+        st.dmax = d;
+    } else {
+        st.problems = 1.0;
+    }
+}
+
 __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
     __shared__ uint2 stack[NN_MAX_LEVELS * NN_THREADS];
     __shared__ StatA warp_part[NN_THREADS / 32];
     const long long i = (long long)blockIdx.x * NN_THREADS + threadIdx.x;
-    const bool active = i < A.n;
     uint2* stk = stack + threadIdx.x;
 
     StatA st;
     st.n = 0.0; st.mean = 0.0; st.m2 = 0.0; st.dmin = DBL_MAX; st.dmax = 0.0; st.problems = 0.0;
     bool fell_back = false;
 
-    if (active) {
-        double qx = A.sx[i], qy = A.sy[i], qz = A.sz[i];
-        if (A.apply_pending && A.state->have_T) {
-            apply_T_point(A.state->T_pending, qx, qy, qz);
-            A.ox[i] = qx;
-            A.oy[i] = qy;
-            A.oz[i] = qz;
+    if (A.worklist) {
+        // second half of mode 4: the queries nn_group_kernel could not settle (already moved, matches untouched)
+        const long long cnt = (long long)*A.work_count;
+        unsigned long long fb = 0, ok = 0;
+        for (long long t = i; t < cnt; t += (long long)gridDim.x * NN_THREADS) {
+            bool f = false;
+            nn_one_query(A, (long long)A.worklist[t], true, stk, st, f);
+            fb += f ? 1ull : 0ull;
+            ok += f ? 0ull : 1ull;
         }
-        const bool finite_q = isfinite(qx) && isfinite(qy) && isfinite(qz);
-        uint32_t pp = NONE, pn = NONE;
-        if (A.mode == 1 && A.prev_pos && A.node_io) {
-            pp = A.prev_pos[i];
-            pn = A.node_io[i];
-        } else if (A.mode == 3 && A.prev_pos) {
-            pp = A.prev_pos[i];
-        }
-        uint32_t result_node = NONE;
-        double best_s;
-        const uint32_t result = per_thread_query<NN_THREADS>(A, qx, qy, qz, finite_q, pp, pn, ICPB_INF, stk, result_node, fell_back,
-                                                             false, &best_s);
-        // findNearest returns index 0 when nothing was accepted (best_idx = 0 initially, octree.cpp:179)
-        const uint32_t pos = (result == NONE) ? A.pos_of_idx0 : result;
-        // computeDistance(p_src, p_tgt) (icpengine.cpp:68-74) = sqrt(dx*dx + dy*dy + dz*dz) with d = src - tgt; the search
-        // evaluated the same sum with d = tgt - src, whose squares are the same doubles, so its value is reused.
-        double d;
-        if (best_s >= 0.0) {
-            d = dsqrt(best_s);
-        } else {
-            double px, py, pz;
-            uint32_t pidx;
-            load_point(A.pts, pos, px, py, pz, pidx);
-            d = dsqrt(sumsq3(dsub(qx, px), dsub(qy, py), dsub(qz, pz)));
-        }
-        A.pos_out[i] = pos;
-        if (A.node_io) A.node_io[i] = result_node;
-        A.dist_out[i] = d;
-        st.n = 1.0;
-        st.mean = d;
-        if (isfinite(d)) {
-            st.dmin = d;
-            st.dmax = d;
-        } else {
-            st.problems = 1.0;
-        }
+        if (A.counters && fb) atomicAdd(&A.counters[1], fb);
+        if (A.counters && ok) atomicAdd(&A.counters[0], ok);
+        return;
     }
+    const bool active = i < A.n;
+    if (active) nn_one_query(A, i, false, stk, st, fell_back);
     if (A.counters && A.mode >= 1) {
         const unsigned fb = __ballot_sync(0xffffffffu, fell_back);
         const unsigned ac = __ballot_sync(0xffffffffu, active);
@@ -122,7 +141,8 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
 
 int nn_grid_blocks(int64_t n) { return (int)((n + NN_THREADS - 1) / NN_THREADS); }
 
-int nn_tile_launch(Ctx* c, const NNArgs& A);  // nn_tile.cu
+int nn_tile_launch(Ctx* c, const NNArgs& A);   // nn_tile.cu
+int nn_group_launch(Ctx* c, const NNArgs& A);  // nn_group.cu
 
 int nn_launch(Ctx* c, const NNLaunch& L) {
     if (L.n <= 0) return ICP_OK;
@@ -136,7 +156,7 @@ int nn_launch(Ctx* c, const NNLaunch& L) {
     A.glmin = c->fast.glev_min;
     A.gnlev = c->fast.glev_n;
     A.gmax_cells = c->opt_walk_max_cells;
-    A.gbias = c->opt_walk_bias;
+    A.gbias = c->opt_walk_bias != -100 ? c->opt_walk_bias : (L.mode == 4 ? 0 : -2);
     A.gcube = c->fast.cube;
     for (int k = 0; k < 4; ++k) {
         A.goff[k] = c->fast.goff[k];
@@ -163,7 +183,28 @@ int nn_launch(Ctx* c, const NNLaunch& L) {
     A.pos_of_idx0 = c->fast.pos_of_idx0;
     A.tile_node = L.tile_node;
     A.terminal_pts = c->opt_terminal_pts;
+    A.worklist = nullptr;
+    A.work_count = nullptr;
     if (L.mode == 2) return nn_tile_launch(c, A);
+    if (L.mode == 4) {
+        // the balanced kernel settles what it can; the per-thread kernel (cell walk, then climb / literal) takes the rest
+        const bool in_place = !L.apply_pending || (L.ox == L.sx && L.oy == L.sy && L.oz == L.sz);
+        if (in_place && c->d_work_count && c->node_io.p) {
+            A.worklist = (uint32_t*)c->node_io.p;
+            A.work_count = c->d_work_count;
+            ICPB_CUDA(c, cudaMemsetAsync(c->d_work_count, 0, sizeof(unsigned int), c->stream));
+            ICPB_TRY(nn_group_launch(c, A));
+            A.mode = 3;
+            A.apply_pending = 0;
+            A.node_io = nullptr;
+            const int blocks = std::min(nn_grid_blocks(L.n), c->sm_count * 7);
+            nn_kernel<<<blocks, NN_THREADS, 0, c->stream>>>(A);
+            c->launches++;
+            ICPB_CUDA(c, cudaGetLastError());
+            return ICP_OK;
+        }
+        A.mode = 3;
+    }
     nn_kernel<<<nn_grid_blocks(L.n), NN_THREADS, 0, c->stream>>>(A);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());

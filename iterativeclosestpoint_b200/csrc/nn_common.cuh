@@ -43,7 +43,10 @@ struct NNArgs {
     int apply_pending;
     int terminal_pts;          // tile kernel: subtrees with at most this many points are staged whole
     int mode;                  // 0: literal traversal from the root; 1: per-thread, climb from the last leaf; 2: warp tiles;
-                               // 3: per-thread, entry through the grid cells the search ball touches
+                               // 3: per-thread, entry through the grid cells the search ball touches;
+                               // 4: as 3, the candidate scan balanced over the warp (nn_group.cu)
+    uint32_t* worklist;        // mode 4: queries the balanced kernel hands to the per-thread kernel ...
+    unsigned int* work_count;  // ... and how many; the per-thread kernel runs over that list when worklist != null
     double init_best;
     uint32_t pos_of_idx0;
 };
@@ -70,14 +73,12 @@ __device__ __forceinline__ NodeRegs load_node(const Node* __restrict__ nodes, ui
     return r;
 }
 
+// One 256-bit load per target point (sm_100a: LDG.E.256): a point is one 32-byte sector, so one request to L1 instead of two.
 __device__ __forceinline__ void load_point(const TPoint* __restrict__ pts, uint32_t i, double& x, double& y, double& z,
                                            uint32_t& idx) {
-    const int4* p = reinterpret_cast<const int4*>(pts + i);
-    int4 a = __ldg(p), b = __ldg(p + 1);
-    x = __hiloint2double(a.y, a.x);
-    y = __hiloint2double(a.w, a.z);
-    z = __hiloint2double(b.y, b.x);
-    idx = (uint32_t)b.z;
+    long long w;
+    asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=l"(w) : "l"(pts + i));
+    idx = (uint32_t)w;
 }
 
 // OctreeNode::minDistanceTo's per-axis term: max(0, max(lo - q, q - hi))   (octree.cpp:34-36)
@@ -355,59 +356,65 @@ __device__ __forceinline__ uint2 grid_entry(const GridView& V, int x, int y, int
     return __ldg(V.g + ((long long)z * V.ny + y) * V.nx + x);
 }
 
+// Seed for a query without a previous match: squared distance to a real target point of q's own base-level cell
+// (clamped into the grid, so queries outside the cloud's box get a seed too) or of a face neighbour; +inf if none.
+__device__ __forceinline__ double walk_seed(const NNArgs& A, const double qx, const double qy, const double qz) {
+    double Sd = ICPB_INF;  // any real target point is a valid seed -- a closer one only makes the walk cheaper
+    const GridView V0 = grid_view(A, 0);
+    int ix = grid_cell_index(A, V0, qx, 0, V0.nx), iy = grid_cell_index(A, V0, qy, 1, V0.ny), iz = grid_cell_index(A, V0, qz, 2, V0.nz);
+    ix = min(max(ix, 0), V0.nx - 1);
+    iy = min(max(iy, 0), V0.ny - 1);
+    iz = min(max(iz, 0), V0.nz - 1);
+    uint2 e = make_uint2(0u, 0u);
+#pragma unroll 1
+    for (int t = 0; t < 7; ++t) {
+        const int dz = (t == 1) ? -1 : (t == 2) ? 1 : 0, dy = (t == 3) ? -1 : (t == 4) ? 1 : 0, dx = (t == 5) ? -1 : (t == 6) ? 1 : 0;
+        const int x = ix + dx, y = iy + dy, z = iz + dz;
+        if (x < 0 || y < 0 || z < 0 || x >= V0.nx || y >= V0.ny || z >= V0.nz) continue;
+        e = grid_entry(V0, x, y, z);
+        if ((e.y >> 30) != 0u) break;
+    }
+    const uint32_t kind = e.y >> 30;
+    if (kind == 0u) return ICPB_INF;
+    uint32_t pt0 = e.x, npts = e.y & 0xFFFFFFu;
+    if (kind == 3u) {
+        uint32_t n = e.x;
+        NodeRegs nd = load_node(A.nodes, n);
+        for (;;) {
+            const uint32_t mask = nd.meta & 0xFFu;
+            if (mask == 0u || nd.npts <= 32u) break;
+            uint32_t oct = 0;
+            oct |= (qx > dmul(dadd(nd.lo[0], nd.hi[0]), 0.5)) ? 1u : 0u;
+            oct |= (qy > dmul(dadd(nd.lo[1], nd.hi[1]), 0.5)) ? 2u : 0u;
+            oct |= (qz > dmul(dadd(nd.lo[2], nd.hi[2]), 0.5)) ? 4u : 0u;
+            if (!((mask >> oct) & 1u)) break;
+            n = nd.child0 + __popc(mask & ((1u << oct) - 1u));
+            nd = load_node(A.nodes, n);
+        }
+        pt0 = nd.pt0;
+        npts = nd.npts;
+    }
+    const uint32_t ns = npts < 32u ? npts : 32u;
+    for (uint32_t k = 0; k < ns; k += 4) {
+        double px[4], py[4], pz[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t kk = (k + j < ns) ? k + j : ns - 1u;
+            uint32_t pidx;
+            load_point(A.pts, pt0 + kk, px[j], py[j], pz[j], pidx);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Sd = fmin(Sd, sumsq3(dsub(px[j], qx), dsub(py[j], qy), dsub(pz[j], qz)));
+    }
+    if (!(Sd < 1e19)) return ICPB_INF;
+    return Sd;
+}
+
 template <int STRIDE>
 __device__ __forceinline__ bool cell_walk(const NNArgs& A, const double qx, const double qy, const double qz, double Sd,
                                           uint2* stk, Fast& F) {
     if (!(Sd < 1e19)) {
-        // no seed yet: take the points of q's own base-level cell (clamped into the grid, so queries outside the
-        // cloud's box get a seed too); if that cell is empty try its six face neighbours.  Any real target point
-        // is a valid seed -- a closer one only makes the walk cheaper.
-        const GridView V0 = grid_view(A, 0);
-        int ix = grid_cell_index(A, V0, qx, 0, V0.nx), iy = grid_cell_index(A, V0, qy, 1, V0.ny), iz = grid_cell_index(A, V0, qz, 2, V0.nz);
-        ix = min(max(ix, 0), V0.nx - 1);
-        iy = min(max(iy, 0), V0.ny - 1);
-        iz = min(max(iz, 0), V0.nz - 1);
-        uint2 e = make_uint2(0u, 0u);
-#pragma unroll 1
-        for (int t = 0; t < 7; ++t) {
-            const int dz = (t == 1) ? -1 : (t == 2) ? 1 : 0, dy = (t == 3) ? -1 : (t == 4) ? 1 : 0, dx = (t == 5) ? -1 : (t == 6) ? 1 : 0;
-            const int x = ix + dx, y = iy + dy, z = iz + dz;
-            if (x < 0 || y < 0 || z < 0 || x >= V0.nx || y >= V0.ny || z >= V0.nz) continue;
-            e = grid_entry(V0, x, y, z);
-            if ((e.y >> 30) != 0u) break;
-        }
-        const uint32_t kind = e.y >> 30;
-        if (kind == 0u) return false;
-        uint32_t pt0 = e.x, npts = e.y & 0xFFFFFFu;
-        if (kind == 3u) {
-            uint32_t n = e.x;
-            NodeRegs nd = load_node(A.nodes, n);
-            for (;;) {
-                const uint32_t mask = nd.meta & 0xFFu;
-                if (mask == 0u || nd.npts <= 32u) break;
-                uint32_t oct = 0;
-                oct |= (qx > dmul(dadd(nd.lo[0], nd.hi[0]), 0.5)) ? 1u : 0u;
-                oct |= (qy > dmul(dadd(nd.lo[1], nd.hi[1]), 0.5)) ? 2u : 0u;
-                oct |= (qz > dmul(dadd(nd.lo[2], nd.hi[2]), 0.5)) ? 4u : 0u;
-                if (!((mask >> oct) & 1u)) break;
-                n = nd.child0 + __popc(mask & ((1u << oct) - 1u));
-                nd = load_node(A.nodes, n);
-            }
-            pt0 = nd.pt0;
-            npts = nd.npts;
-        }
-        const uint32_t ns = npts < 32u ? npts : 32u;
-        for (uint32_t k = 0; k < ns; k += 4) {
-            double px[4], py[4], pz[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t kk = (k + j < ns) ? k + j : ns - 1u;
-                uint32_t pidx;
-                load_point(A.pts, pt0 + kk, px[j], py[j], pz[j], pidx);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) Sd = fmin(Sd, sumsq3(dsub(px[j], qx), dsub(py[j], qy), dsub(pz[j], qz)));
-        }
+        Sd = walk_seed(A, qx, qy, qz);
         if (!(Sd < 1e19)) return false;
     }
     const double r = dmul(dsqrt(Sd), 1.0 + 9.5367431640625e-07);  // sqrt(S) (1 + 2^-20)

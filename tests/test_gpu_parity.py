@@ -58,7 +58,7 @@ def test_octree_structure_bit_exact(handle, oracle, name, make, leaf, depth):
     assert info.depth == int(want["depth"].max())
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3], ids=["literal", "climb", "tile", "walk"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4], ids=["literal", "climb", "tile", "walk", "group"])
 @pytest.mark.parametrize("name,make,leaf,depth", TREE_CASES, ids=[c[0] for c in TREE_CASES])
 def test_nn_indices_bit_exact(handle, oracle, name, make, leaf, depth, mode):
     tgt = make()
@@ -76,7 +76,7 @@ def test_nn_indices_bit_exact(handle, oracle, name, make, leaf, depth, mode):
         assert np.array_equal(dist, d), f"{name}/{qname}: distances are not bit-identical"
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3], ids=["literal", "climb", "tile", "walk"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4], ids=["literal", "climb", "tile", "walk", "group"])
 def test_nn_lattice_ties_follow_reference_traversal_order(handle, oracle, mode):
     """Exactly equidistant candidates: the winner is the first one the reference's DFS visits, not the lowest index."""
     lat = clouds.lattice_exact()
@@ -232,7 +232,7 @@ def _check_run(got, want, n_src, tol=REL_E2E):
         assert np.max(np.abs(got.finalT - want.final_t)) <= tol * max(1.0, float(np.max(np.abs(want.final_t))))
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3], ids=["literal", "climb", "tile", "walk"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4], ids=["literal", "climb", "tile", "walk", "group"])
 def test_register_config1_engine(handle, oracle, mode):
     """BASELINE.json config #1: 10k-point cloud vs transformed + noised copy, 50 / 1e-6 / 3 sigma / 10 / 20."""
     src, tgt = synth.make_test_icp_pair(10000)
@@ -431,11 +431,12 @@ def test_full_size_config3_sample_parity_and_properties(handle, oracle):
         assert np.array_equal(idx[sample], want)
     dv = src - tgt[idx]
     assert np.array_equal(dist, np.sqrt(dv[:, 0] * dv[:, 0] + dv[:, 1] * dv[:, 1] + dv[:, 2] * dv[:, 2]))
-    handle.set_option("nn_mode", 1)
-    idx1, dist1, _ = handle.nn_query(src)
-    assert np.array_equal(idx1, idx) and np.array_equal(dist1, dist)
+    for other in (1, 3):
+        handle.set_option("nn_mode", other)
+        idx1, dist1, _ = handle.nn_query(src)
+        assert np.array_equal(idx1, idx) and np.array_equal(dist1, dist)
     # a few iterations of the registration itself, then the same check on the moved cloud
-    handle.set_option("nn_mode", 3)
+    handle.set_option("nn_mode", 4)
     handle.set_params(ICPParameters(maxIterations=3))
     moved = src.copy()
     res = handle.register(moved, tgt)
