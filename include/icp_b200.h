@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ICP_B200_ABI_VERSION 1
+#define ICP_B200_ABI_VERSION 2
 
 typedef struct icp_b200_ctx* icp_handle;
 
@@ -38,7 +38,9 @@ typedef enum icp_status {
     ICP_INVALID_ARGUMENT = 4,
     ICP_CUDA_ERROR = 5,
     ICP_NCCL_ERROR = 6,
-    ICP_NO_OCTREE = 7         /* stage call issued before icp_octree_build */
+    ICP_NO_OCTREE = 7,        /* stage call issued before icp_octree_build */
+    ICP_IO_ERROR = 8,         /* core/lasio.cpp:9-12,23-27,134-137: file cannot be opened / read / created */
+    ICP_BAD_FORMAT = 9        /* core/lasio.cpp:30-34 "不是有效的LAS文件"; icp_registration.cpp:291-295 implausible point count */
 } icp_status;
 
 /* The engine (PointCloudRegistration/core/) and the CLI program (icp_registration.cpp) implement the same
@@ -192,6 +194,75 @@ int icp_nn_counters(icp_handle h, int64_t* fast_path, int64_t* literal_fallback,
 /* Tile kernel (nn_mode 2): lanes a tile could not prove and handed to the per-thread search, and the number of
  * (tile, candidate) pairs scanned -- candidates per query = candidates_scanned / queries. */
 int icp_nn_tile_counters(icp_handle h, int64_t* per_thread_lanes, int64_t* candidates_scanned, int reset);
+
+/* ---- data formats either side of the loop ------------------------------------ */
+#define ICP_LAS_HEADER_BYTES 227   /* LAS 1.2 public header block as both reference readers/writers use it */
+#define ICP_LAS_RECORD_BYTES 20    /* point data record format 0, what both reference writers emit */
+
+/* The header fields the reference reads (core/lasio.cpp:38-48; icp_registration.cpp:282-305) and writes (:140-184). */
+typedef struct icp_las_header {
+    uint32_t offset_to_data;    /* byte 96  */
+    uint32_t n_points;          /* byte 107 */
+    uint16_t record_length;     /* byte 105 */
+    uint16_t pad_[3];
+    double scale[3];            /* bytes 131, 139, 147 */
+    double offset[3];           /* bytes 155, 163, 171 */
+    double min[3], max[3];      /* bytes 187/203/219 and 179/195/211 */
+} icp_las_header;
+
+/* LAS point records still in file form: n records `record_length` bytes apart, X/Y/Z = the first three int32. */
+typedef struct icp_las_points {
+    const uint8_t* records;
+    int64_t n;
+    int32_t record_length;
+    int32_t pad_;
+    double scale[3], offset[3];
+} icp_las_points;
+
+/* Header parsing; ICP_BAD_FORMAT unless the block starts with "LASF" (lasio.cpp:30-34).  Host only, no handle. */
+int icp_las_parse_header(const uint8_t* header227, icp_las_header* out);
+/* The point loop of LASIO::readLAS / readLASBatch (lasio.cpp:86-104, 268-287) and of readLASFile
+ * (icp_registration.cpp:347-362) on the device: p = raw * scale + offset per axis.  12 B read, 24 B written per point. */
+int icp_las_decode(icp_handle h, const uint8_t* records, int64_t n, int32_t record_length, const double* scale3,
+                   const double* offset3, double* xyz_out);
+/* The point loop of LASIO::writeLAS (lasio.cpp:192-204) and saveResultAsLAS (icp_registration.cpp:783-810):
+ * (int32)((p - offset) / scale) with the reference's truncating cast, 8 zero bytes; 20-byte records out. */
+int icp_las_encode(icp_handle h, const double* xyz, int64_t n, const double* scale3, const double* offset3,
+                   uint8_t* records_out);
+/* PointCloud::computeBounds (core/pointcloud.cpp:24-45); all zero for an empty cloud. */
+int icp_cloud_bounds(icp_handle h, const double* xyz, int64_t n, double* min3, double* max3);
+/* The bytes LASIO::writeLAS (variant ENGINE: scale 0.001, offset = cloud minimum; scale3/offset3 ignored) or
+ * saveResultAsLAS (variant CLI: the cloud's own scale/offset) would put in the file.  `bytes_out` always receives the
+ * size needed (227 + 20 n); ICP_EMPTY_INPUT for an empty cloud (lasio.cpp:128-131). */
+int icp_las_file_image(icp_handle h, const double* xyz, int64_t n, int variant, const double* scale3, const double* offset3,
+                       uint8_t* image_out, int64_t cap, int64_t* bytes_out);
+/* LASIO::writeLAS(filename, cloud) (lasio.h:31) / saveResultAsLAS(cloud, filename) (icp_registration.cpp:698). */
+int icp_las_write(icp_handle h, const char* path, const double* xyz, int64_t n, int variant, const double* scale3,
+                  const double* offset3);
+/* LASIO::readLAS(filename, cloud, maxPoints) (lasio.h:23; variant ENGINE) / readLASFile(filename, cloud)
+ * (icp_registration.cpp:248; variant CLI: no signature check, point count must be 1..1e8, max_points ignored).
+ * With xyz_out == NULL only the header is read and *n_out receives the number of points a full call returns.
+ * A truncated point block is ICP_IO_ERROR (the reference would parse stale buffer contents). */
+int icp_las_read(icp_handle h, const char* path, int64_t max_points, int variant, icp_las_header* header_out,
+                 double* xyz_out, int64_t cap, int64_t* n_out);
+/* PointCloud::downsample(targetSize) (core/pointcloud.cpp:107-128): point (int)(i * size / target) for i < target, the
+ * whole cloud when it is not larger than target; ICP_EMPTY_INPUT where the reference returns nullptr. */
+int icp_downsample(icp_handle h, const double* xyz, int64_t n, int32_t target_size, double* xyz_out, int64_t* n_out);
+/* The CLI's 1-in-k sampling (icp_registration.cpp:857,877-882): points 0, k, 2k, ... */
+int icp_downsample_stride(icp_handle h, const double* xyz, int64_t n, int64_t stride, double* xyz_out, int64_t* n_out);
+/* Iteration replay of the viewer (widgets/pointcloudviewer.cpp:86-116): xyz_out = original cloud moved by one
+ * IterationResult::transform through PointCloud::applyTransform (core/pointcloud.cpp:73-86); T16 == NULL is the
+ * viewer's index -1 (the untouched original).  xyz_out may alias original_xyz. */
+int icp_replay_iteration(icp_handle h, const double* original_xyz, int64_t n, const double* T16, double* xyz_out);
+/* saveTransformation(R, t, filename, &iteration_transforms) (icp_registration.cpp:625-695): the CLI's text report,
+ * byte for byte (ostream precision 10).  iteration_T16: n_iterations row-major 4x4 matrices, may be NULL.  Host only. */
+int icp_save_transformation(const char* path, const double* R9, const double* t3, const double* iteration_T16,
+                            int32_t n_iterations);
+/* icp_register on clouds that are still LAS point records: the records go to the device as they are (12-34 B per point
+ * instead of 24), are decoded there (lasio.cpp:92-99) and feed the loop directly.  The registered source is written to
+ * src_out_xyz (n x 3, may be NULL) on the exits where the reference writes its source back. */
+int icp_register_las(icp_handle h, const icp_las_points* src, const icp_las_points* tgt, icp_result* out,
+                     double* src_out_xyz, const volatile int* stop_flag);
 
 /* Number of kernels this library has launched on the handle since creation (bench.py's gpu_launches). */
 int64_t icp_kernel_launches(icp_handle h);

@@ -19,8 +19,12 @@ ICP_INVALID_ARGUMENT = 4
 ICP_CUDA_ERROR = 5
 ICP_NCCL_ERROR = 6
 ICP_NO_OCTREE = 7
+ICP_IO_ERROR = 8
+ICP_BAD_FORMAT = 9
 STATUS_NAMES = {0: "OK", 1: "EMPTY_INPUT", 2: "CANCELLED", 3: "TOO_FEW_INLIERS", 4: "INVALID_ARGUMENT",
-                5: "CUDA_ERROR", 6: "NCCL_ERROR", 7: "NO_OCTREE"}
+                5: "CUDA_ERROR", 6: "NCCL_ERROR", 7: "NO_OCTREE", 8: "IO_ERROR", 9: "BAD_FORMAT"}
+LAS_HEADER_BYTES = 227
+LAS_RECORD_BYTES = 20
 
 VARIANT_ENGINE = 0
 VARIANT_CLI = 1
@@ -33,6 +37,9 @@ EXPORTED = [
     "icp_iteration_stats", "icp_best_fit_transform", "icp_solve_from_H", "icp_apply_transform",
     "icp_comm_unique_id", "icp_comm_init", "icp_comm_destroy", "icp_register_sharded", "icp_register_batch",
     "icp_kernel_launches", "icp_nn_counters", "icp_nn_tile_counters",
+    "icp_las_parse_header", "icp_las_decode", "icp_las_encode", "icp_cloud_bounds", "icp_las_file_image", "icp_las_write",
+    "icp_las_read", "icp_downsample", "icp_downsample_stride", "icp_replay_iteration", "icp_save_transformation",
+    "icp_register_las",
 ]
 
 
@@ -72,6 +79,17 @@ class IcpOctreeInfo(C.Structure):
                 ("search_nodes", C.c_int64), ("search_node_bytes", C.c_int64), ("grid_bytes", C.c_int64),
                 ("search_depth", C.c_int32), ("grid_base_level", C.c_int32), ("grid_fine_level", C.c_int32),
                 ("pad3_", C.c_int32), ("grid_base_cell", C.c_double)]
+
+
+class IcpLasHeader(C.Structure):
+    _fields_ = [("offset_to_data", C.c_uint32), ("n_points", C.c_uint32), ("record_length", C.c_uint16),
+                ("pad_", C.c_uint16 * 3), ("scale", C.c_double * 3), ("offset", C.c_double * 3),
+                ("min", C.c_double * 3), ("max", C.c_double * 3)]
+
+
+class IcpLasPoints(C.Structure):
+    _fields_ = [("records", C.c_void_p), ("n", C.c_int64), ("record_length", C.c_int32), ("pad_", C.c_int32),
+                ("scale", C.c_double * 3), ("offset", C.c_double * 3)]
 
 
 ITERATION_CB = C.CFUNCTYPE(None, C.POINTER(IcpIteration), C.c_void_p)
@@ -128,6 +146,19 @@ def load() -> C.CDLL:
     L.icp_register_batch.argtypes = [vp, C.c_int32, vp, vp, vp, vp, C.POINTER(IcpResult)]
     L.icp_nn_counters.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
     L.icp_nn_tile_counters.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
+    i64p = C.POINTER(C.c_int64)
+    L.icp_las_parse_header.argtypes = [vp, C.POINTER(IcpLasHeader)]
+    L.icp_las_decode.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, vp, vp]
+    L.icp_las_encode.argtypes = [vp, vp, C.c_int64, vp, vp, vp]
+    L.icp_cloud_bounds.argtypes = [vp, vp, C.c_int64, vp, vp]
+    L.icp_las_file_image.argtypes = [vp, vp, C.c_int64, C.c_int, vp, vp, vp, C.c_int64, i64p]
+    L.icp_las_write.argtypes = [vp, C.c_char_p, vp, C.c_int64, C.c_int, vp, vp]
+    L.icp_las_read.argtypes = [vp, C.c_char_p, C.c_int64, C.c_int, C.POINTER(IcpLasHeader), vp, C.c_int64, i64p]
+    L.icp_downsample.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, i64p]
+    L.icp_downsample_stride.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, i64p]
+    L.icp_replay_iteration.argtypes = [vp, vp, C.c_int64, vp, vp]
+    L.icp_save_transformation.argtypes = [C.c_char_p, vp, vp, vp, C.c_int32]
+    L.icp_register_las.argtypes = [vp, C.POINTER(IcpLasPoints), C.POINTER(IcpLasPoints), C.POINTER(IcpResult), vp, vp]
     L.icp_kernel_launches.argtypes = [vp]
     L.icp_kernel_launches.restype = C.c_int64
     _lib = L

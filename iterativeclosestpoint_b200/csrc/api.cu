@@ -373,10 +373,25 @@ static void init_result(icp_result* out) {
     identity16(out->last_T);
 }
 
+// Stages one cloud on the device as AoS doubles: either a plain copy of xyz, or -- when `las` is given -- a copy of the
+// raw LAS records followed by the decode kernel (cloudio.cu), so only the records cross PCIe.
+static int stage_cloud(Ctx* c, cudaStream_t st, DevBuf& dst, DevBuf& rec_stage, const double* xyz, const icp_las_points* las, int64_t n) {
+    ICPB_TRY(devbuf_reserve(c, dst, (size_t)n * 3 * sizeof(double)));
+    if (!las) {
+        ICPB_CUDA(c, cudaMemcpyAsync(dst.p, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+        return ICP_OK;
+    }
+    const size_t bytes = (size_t)n * (size_t)las->record_length;
+    ICPB_TRY(devbuf_reserve(c, rec_stage, bytes));
+    ICPB_CUDA(c, cudaMemcpyAsync(rec_stage.p, las->records, bytes, cudaMemcpyHostToDevice, st));
+    return las_decode_launch(c, st, (const uint8_t*)rec_stage.p, n, las->record_length, las->scale, las->offset, (double*)dst.p);
+}
+
 static int register_impl(Ctx* c, double* src_xyz, int64_t n_src, int64_t n_src_global, const double* tgt_xyz, int64_t n_tgt,
-                         icp_result* out, const volatile int* stop_flag) {
+                         icp_result* out, const volatile int* stop_flag, const icp_las_points* src_las = nullptr,
+                         const icp_las_points* tgt_las = nullptr) {
     init_result(out);
-    if (!src_xyz || !tgt_xyz || n_src_global <= 0 || n_tgt <= 0) {  // icpengine.cpp:26-34
+    if ((!src_xyz && !src_las) || (!tgt_xyz && !tgt_las) || n_src_global <= 0 || n_tgt <= 0) {  // icpengine.cpp:26-34
         out->status = ICP_EMPTY_INPUT;
         return ICP_EMPTY_INPUT;
     }
@@ -389,15 +404,16 @@ static int register_impl(Ctx* c, double* src_xyz, int64_t n_src, int64_t n_src_g
     log_msg(c, "target: %lld points", (long long)n_tgt);
 
     ICPB_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
-    ICPB_TRY(upload(c, c->tgt_raw, tgt_xyz, n_tgt));
+    ICPB_TRY(stage_cloud(c, c->stream, c->tgt_raw, c->las_tgt, tgt_xyz, tgt_las, n_tgt));
     c->n_tgt = n_tgt;
     // the source goes up on a second stream so that (from pinned memory) its copy overlaps the target's tree build
     DevBuf& src_stage = c->scratch_src;
     ICPB_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
     if (n_src > 0) {
         ICPB_TRY(devbuf_reserve(c, src_stage, (size_t)n_src * 3 * sizeof(double)));
+        if (src_las) ICPB_TRY(devbuf_reserve(c, c->las_src, (size_t)n_src * (size_t)src_las->record_length));
         ICPB_CUDA(c, cudaStreamWaitEvent(c->stream2, c->ev[5], 0));  // after the target copy: one copy engine direction, FIFO
-        ICPB_CUDA(c, cudaMemcpyAsync(src_stage.p, src_xyz, (size_t)n_src * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream2));
+        ICPB_TRY(stage_cloud(c, c->stream2, src_stage, c->las_src, src_xyz, src_las, n_src));
         ICPB_CUDA(c, cudaEventRecord(c->ev_src, c->stream2));
     }
     log_msg(c, "building the target octree ...");
@@ -415,7 +431,7 @@ static int register_impl(Ctx* c, double* src_xyz, int64_t n_src, int64_t n_src_g
     bool write_back = true;
     ICPB_TRY(run_loop(c, n_src_global, out, stop_flag, &write_back));
     ICPB_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
-    if (write_back && n_src > 0) ICPB_TRY(write_back_source(c, src_xyz, n_src));  // icpengine.cpp:371-375
+    if (write_back && n_src > 0 && src_xyz) ICPB_TRY(write_back_source(c, src_xyz, n_src));  // icpengine.cpp:371-375
     cudaEvent_t end;
     ICPB_CUDA(c, cudaEventCreate(&end));
     ICPB_CUDA(c, cudaEventRecord(end, c->stream));
@@ -496,7 +512,7 @@ void icp_destroy(icp_handle h) {
     c->workers.clear();
     octree_free(c);
     DevBuf* bufs[] = {&c->tgt_raw, &c->sx, &c->sy, &c->sz, &c->sperm, &c->pos, &c->dist, &c->mask, &c->part_a, &c->part_b,
-                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io};
+                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt};
     for (DevBuf* b : bufs) devbuf_free(*b);
     if (c->pin_a.p) cudaFreeHost(c->pin_a.p);
     if (c->pin_b.p) cudaFreeHost(c->pin_b.p);
@@ -625,6 +641,23 @@ int icp_register(icp_handle h, double* src_xyz, int64_t n_src, const double* tgt
         return ICP_INVALID_ARGUMENT;
     }
     return register_impl(c, src_xyz, n_src, n_src, tgt_xyz, n_tgt, out, stop_flag);
+}
+
+int icp_register_las(icp_handle h, const icp_las_points* src, const icp_las_points* tgt, icp_result* out, double* src_out_xyz,
+                     const volatile int* stop_flag) {
+    Ctx* c = (Ctx*)h;
+    if (!c || !out) return ICP_INVALID_ARGUMENT;
+    if (c->n_ranks > 1) {
+        c->err = "icp_register_las on a handle with an initialised communicator";
+        return ICP_INVALID_ARGUMENT;
+    }
+    if (!src || !tgt || !src->records || !tgt->records || src->n <= 0 || tgt->n <= 0) {  // icpengine.cpp:26-34
+        init_result(out);
+        out->status = ICP_EMPTY_INPUT;
+        return ICP_EMPTY_INPUT;
+    }
+    if (src->record_length < 12 || tgt->record_length < 12) return ICP_INVALID_ARGUMENT;
+    return register_impl(c, src_out_xyz, src->n, src->n, nullptr, tgt->n, out, stop_flag, src, tgt);
 }
 
 int icp_register_sharded(icp_handle h, double* src_shard_xyz, int64_t n_shard, int64_t n_src_global, const double* tgt_xyz,

@@ -80,6 +80,7 @@ struct Ctx {
     DevBuf node_io;            // per-query leaf of the last match (temporal start of the next search)
     DevBuf part_a, part_b;     // per-block partials
     DevBuf scratch0, scratch1, scratch2, scratch3, scratch_src;
+    DevBuf las_src, las_tgt;   // raw LAS point records of icp_register_las, decoded on the device (cloudio.cu)
     bool src_identity_perm = false;  // resident source is in caller order (no permutation)
     bool prev_valid = false;         // pos / node_io hold last run's matches of the resident source against the current tree
     float last_build_ms = 0.f;
@@ -157,6 +158,10 @@ struct NNLaunch {
 };
 int nn_launch(Ctx* c, const NNLaunch& L);
 int nn_grid_blocks(int64_t n);
+
+// cloudio.cu
+int las_decode_launch(Ctx* c, cudaStream_t st, const uint8_t* d_rec, int64_t n, int rl, const double* scale, const double* offset,
+                      double* d_xyz);
 
 // iter.cu
 int apply_aos_launch(Ctx* c, const double* d_T16, double* xyz, int64_t n);

@@ -195,6 +195,7 @@ int nn_launch(Ctx* c, const NNLaunch& L) {
             ICPB_CUDA(c, cudaMemsetAsync(c->d_work_count, 0, sizeof(unsigned int), c->stream));
             ICPB_TRY(nn_group_launch(c, A));
             A.mode = 3;
+            if (c->opt_walk_bias == -100) A.gbias = -2;
             A.apply_pending = 0;
             A.node_io = nullptr;
             const int blocks = std::min(nn_grid_blocks(L.n), c->sm_count * 7);

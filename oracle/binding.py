@@ -468,3 +468,192 @@ class RefCli:
         t = np.ascontiguousarray(t, dtype=np.float64)
         its = np.ascontiguousarray(its, dtype=np.float64).reshape(-1, 16)
         self.lib.ref_cli_save_transformation(_d(R), _d(t), _d(its), len(its), filename.encode())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Data-format steps either side of the loop: LAS decode / encode, bounds, downsampling,
+# replay, transformation report.  OracleIO = cloudio_oracle.c (this repo's restatement); RefIO = the unmodified
+# reference (oracle/_ref/libref_io.so + the CLI's functions in libref_cli.so).
+# ---------------------------------------------------------------------------------------------------------
+REF_IO_SO = os.path.join(HERE, "_ref", "libref_io.so")
+LAS_HEADER_BYTES = 227
+LAS_RECORD_BYTES = 20
+
+
+def _u8(a):
+    return a.ctypes.data_as(_u8p)
+
+
+class OracleIO:
+    def __init__(self, path: str | None = None):
+        self.lib = C.CDLL(path or build_oracle())
+        L = self.lib
+        L.orc_las_decode.argtypes = [_u8p, C.c_int64, C.c_int32, _dp, _dp, _dp]
+        L.orc_las_encode.argtypes = [_dp, C.c_int64, _dp, _dp, _u8p]
+        L.orc_bounds.argtypes = [_dp, C.c_int64, _dp, _dp]
+        L.orc_las_file_image.restype = C.c_int64
+        L.orc_las_file_image.argtypes = [C.c_int, _dp, C.c_int64, _dp, _dp, _u8p]
+        L.orc_las_parse_header.restype = C.c_int
+        L.orc_las_parse_header.argtypes = [_u8p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint16), _dp, _dp]
+        L.orc_downsample.restype = C.c_int64
+        L.orc_downsample.argtypes = [_dp, C.c_int64, C.c_int32, _dp]
+        L.orc_downsample_stride.restype = C.c_int64
+        L.orc_downsample_stride.argtypes = [_dp, C.c_int64, C.c_int64, _dp]
+        L.orc_cloud_apply.argtypes = [_dp, _dp, C.c_int64, _dp]
+        L.orc_transformation_text.restype = C.c_int64
+        L.orc_transformation_text.argtypes = [_dp, _dp, _dp, C.c_int32, C.c_char_p, C.c_int64]
+
+    def las_decode(self, records, n, record_length, scale, offset):
+        records = np.ascontiguousarray(records, dtype=np.uint8)
+        scale = np.ascontiguousarray(scale, dtype=np.float64); offset = np.ascontiguousarray(offset, dtype=np.float64)
+        out = np.empty((n, 3))
+        self.lib.orc_las_decode(_u8(records), n, record_length, _d(scale), _d(offset), _d(out))
+        return out
+
+    def las_encode(self, xyz, scale, offset):
+        xyz = _c3(xyz)
+        scale = np.ascontiguousarray(scale, dtype=np.float64); offset = np.ascontiguousarray(offset, dtype=np.float64)
+        out = np.empty(len(xyz) * LAS_RECORD_BYTES, dtype=np.uint8)
+        self.lib.orc_las_encode(_d(xyz), len(xyz), _d(scale), _d(offset), _u8(out))
+        return out
+
+    def bounds(self, xyz):
+        xyz = _c3(xyz)
+        mn = np.empty(3); mx = np.empty(3)
+        self.lib.orc_bounds(_d(xyz), len(xyz), _d(mn), _d(mx))
+        return mn, mx
+
+    def las_file_image(self, xyz, variant=VARIANT_ENGINE, scale=(0.001,) * 3, offset=(0.0,) * 3):
+        xyz = _c3(xyz)
+        scale = np.ascontiguousarray(scale, dtype=np.float64); offset = np.ascontiguousarray(offset, dtype=np.float64)
+        out = np.empty(LAS_HEADER_BYTES + LAS_RECORD_BYTES * len(xyz), dtype=np.uint8)
+        n = self.lib.orc_las_file_image(variant, _d(xyz), len(xyz), _d(scale), _d(offset), _u8(out))
+        return out[:n]
+
+    def las_parse_header(self, header):
+        header = np.ascontiguousarray(header, dtype=np.uint8)
+        off = C.c_uint32(); n = C.c_uint32(); rl = C.c_uint16()
+        scale = np.empty(3); offset = np.empty(3)
+        ok = self.lib.orc_las_parse_header(_u8(header), C.byref(off), C.byref(n), C.byref(rl), _d(scale), _d(offset))
+        return bool(ok), off.value, n.value, rl.value, scale, offset
+
+    def las_read_image(self, image, max_points=0):
+        """What LASIO::readLAS returns for a file with these bytes."""
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        ok, off, n, rl, scale, offset = self.las_parse_header(image[:LAS_HEADER_BYTES])
+        if not ok:
+            return None
+        if max_points and max_points < n:
+            n = max_points
+        return self.las_decode(image[off:off + n * rl], n, rl, scale, offset)
+
+    def downsample(self, xyz, target):
+        xyz = _c3(xyz)
+        out = np.empty((max(min(len(xyz), max(target, 0)), 1), 3))
+        n = self.lib.orc_downsample(_d(xyz), len(xyz), target, _d(out))
+        return out[:n]
+
+    def downsample_stride(self, xyz, stride):
+        xyz = _c3(xyz)
+        out = np.empty((len(xyz) // max(stride, 1) + 1, 3))
+        n = self.lib.orc_downsample_stride(_d(xyz), len(xyz), stride, _d(out))
+        return out[:n]
+
+    def cloud_apply(self, T, xyz):
+        xyz = _c3(xyz)
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        out = np.empty_like(xyz)
+        self.lib.orc_cloud_apply(_d(T), _d(xyz), len(xyz), _d(out))
+        return out
+
+    def transformation_text(self, R, t, its=None) -> bytes:
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(9)
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        its = np.zeros((0, 16)) if its is None else np.ascontiguousarray(its, dtype=np.float64).reshape(-1, 16)
+        need = self.lib.orc_transformation_text(_d(R), _d(t), _d(its) if len(its) else None, len(its), None, 0)
+        buf = C.create_string_buffer(need + 1)
+        self.lib.orc_transformation_text(_d(R), _d(t), _d(its) if len(its) else None, len(its), buf, need + 1)
+        return buf.raw[:need]
+
+
+def ref_io_available() -> bool:
+    return os.path.exists(REF_IO_SO) and os.path.exists(REF_CLI_SO)
+
+
+class RefIO:
+    """The unmodified reference: LASIO / PointCloud (engine) and readLASFile / saveResultAsLAS / saveTransformation (CLI)."""
+
+    def __init__(self):
+        self.lib = C.CDLL(REF_IO_SO)
+        self.cli = C.CDLL(REF_CLI_SO)
+        L = self.lib
+        L.ref_io_write_las.restype = C.c_int
+        L.ref_io_write_las.argtypes = [C.c_char_p, _dp, C.c_int64]
+        L.ref_io_read_las.restype = C.c_int64
+        L.ref_io_read_las.argtypes = [C.c_char_p, C.c_int64, _dp, C.c_int64, _dp]
+        L.ref_io_read_las_batch.restype = C.c_int64
+        L.ref_io_read_las_batch.argtypes = [C.c_char_p, C.c_int64, _dp, C.c_int64, _i64p, C.c_int64, _i64p]
+        L.ref_io_bounds.argtypes = [_dp, C.c_int64, _dp, _dp]
+        L.ref_io_downsample.restype = C.c_int64
+        L.ref_io_downsample.argtypes = [_dp, C.c_int64, C.c_int, _dp, C.c_int64]
+        L.ref_io_apply_transform.argtypes = [_dp, _dp, _dp, C.c_int64]
+        K = self.cli
+        K.ref_cli_read_las.restype = C.c_int64
+        K.ref_cli_read_las.argtypes = [C.c_char_p, _dp, C.c_int64, _dp, _dp]
+        K.ref_cli_save_las.argtypes = [_dp, C.c_int64, _dp, _dp, C.c_char_p]
+        K.ref_cli_save_transformation.argtypes = [_dp, _dp, _dp, C.c_int, C.c_char_p]
+
+    def write_las(self, path, xyz) -> bool:
+        xyz = _c3(xyz)
+        return bool(self.lib.ref_io_write_las(path.encode(), _d(xyz), len(xyz)))
+
+    def read_las(self, path, max_points=0):
+        b = np.empty(6)
+        n = self.lib.ref_io_read_las(path.encode(), max_points, None, 0, _d(b))
+        if n < 0:
+            return None, None
+        out = np.empty((n, 3))
+        self.lib.ref_io_read_las(path.encode(), max_points, _d(out), n, _d(b))
+        return out, b
+
+    def read_las_batch(self, path, batch_size, cap):
+        out = np.empty((cap, 3)); sizes = np.zeros(cap + 1, dtype=np.int64); nb = C.c_int64()
+        n = self.lib.ref_io_read_las_batch(path.encode(), batch_size, _d(out), cap, sizes.ctypes.data_as(_i64p), len(sizes), C.byref(nb))
+        return out[:n], sizes[:nb.value]
+
+    def bounds(self, xyz):
+        xyz = _c3(xyz)
+        mn = np.empty(3); mx = np.empty(3)
+        self.lib.ref_io_bounds(_d(xyz), len(xyz), _d(mn), _d(mx))
+        return mn, mx
+
+    def downsample(self, xyz, target):
+        xyz = _c3(xyz)
+        out = np.empty((max(len(xyz), 1), 3))
+        n = self.lib.ref_io_downsample(_d(xyz), len(xyz), target, _d(out), len(out))
+        return None if n < 0 else out[:n]
+
+    def apply_transform(self, R, t, xyz):
+        xyz = _c3(xyz).copy()
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(9); t = np.ascontiguousarray(t, dtype=np.float64)
+        self.lib.ref_io_apply_transform(_d(R), _d(t), _d(xyz), len(xyz))
+        return xyz
+
+    def cli_read_las(self, path):
+        s = np.empty(3); o = np.empty(3)
+        n = self.cli.ref_cli_read_las(path.encode(), None, 0, _d(s), _d(o))
+        if n < 0:
+            return None, None, None
+        out = np.empty((n, 3))
+        self.cli.ref_cli_read_las(path.encode(), _d(out), n, _d(s), _d(o))
+        return out, s, o
+
+    def cli_save_las(self, path, xyz, scale, offset):
+        xyz = _c3(xyz)
+        scale = np.ascontiguousarray(scale, dtype=np.float64); offset = np.ascontiguousarray(offset, dtype=np.float64)
+        self.cli.ref_cli_save_las(_d(xyz), len(xyz), _d(scale), _d(offset), path.encode())
+
+    def cli_save_transformation(self, path, R, t, its=None):
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(9); t = np.ascontiguousarray(t, dtype=np.float64)
+        its = np.zeros((0, 16)) if its is None else np.ascontiguousarray(its, dtype=np.float64).reshape(-1, 16)
+        self.cli.ref_cli_save_transformation(_d(R), _d(t), _d(its) if len(its) else None, len(its), path.encode())

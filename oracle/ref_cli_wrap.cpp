@@ -121,4 +121,38 @@ void ref_cli_save_transformation(const double* R9, const double* t3, const doubl
     std::cout.rdbuf(old);
 }
 
+// readLASFile (icp_registration.cpp:248-378): returns the point count (-1 on failure), the file's scale / offset as the
+// CLI keeps them on the cloud (:307-312), and up to cap points.
+int64_t ref_cli_read_las(const char* filename, double* xyz_out, int64_t cap, double* scale3, double* offset3) {
+    refcli::PointCloud c;
+    std::streambuf *old = std::cout.rdbuf(), *olde = std::cerr.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
+    std::cerr.rdbuf(sink.rdbuf());
+    const bool ok = refcli::readLASFile(std::string(filename), c);
+    std::cout.rdbuf(old);
+    std::cerr.rdbuf(olde);
+    if (!ok) return -1;
+    scale3[0] = c.x_scale; scale3[1] = c.y_scale; scale3[2] = c.z_scale;
+    offset3[0] = c.x_offset; offset3[1] = c.y_offset; offset3[2] = c.z_offset;
+    for (size_t i = 0; i < c.points.size() && (int64_t)i < cap; ++i) {
+        xyz_out[3 * i] = c.points[i].x; xyz_out[3 * i + 1] = c.points[i].y; xyz_out[3 * i + 2] = c.points[i].z;
+    }
+    return (int64_t)c.points.size();
+}
+
+// saveResultAsLAS (icp_registration.cpp:698-815) with the cloud's scale / offset set as main() does (:864-875).
+void ref_cli_save_las(const double* xyz, int64_t n, const double* scale3, const double* offset3, const char* filename) {
+    refcli::PointCloud c;
+    c.points.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) c.points[(size_t)i] = refcli::Point3D(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    c.x_scale = scale3[0]; c.y_scale = scale3[1]; c.z_scale = scale3[2];
+    c.x_offset = offset3[0]; c.y_offset = offset3[1]; c.z_offset = offset3[2];
+    std::streambuf* old = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
+    refcli::saveResultAsLAS(c, std::string(filename));
+    std::cout.rdbuf(old);
+}
+
 }  // extern "C"

@@ -41,15 +41,16 @@ def test_library_exports_every_declared_symbol():
     L = lib.load()
     for name in declared_symbols():
         assert hasattr(L, name), f"libicp_b200.so does not export {name}"
-    assert L.icp_abi_version() == 1
+    assert L.icp_abi_version() == 2
 
 
 def test_struct_layouts_match_header_sizes():
     """ctypes mirrors of the header structs: sizes a C compiler gives the header's definitions."""
     lib = _lib()
     cc = shutil.which("gcc") or "/usr/bin/gcc"
-    prog = ('#include <stdio.h>\n#include "icp_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(icp_params),'
-            'sizeof(icp_iteration), sizeof(icp_stats), sizeof(icp_result), sizeof(icp_octree_info));return 0;}\n')
+    prog = ('#include <stdio.h>\n#include "icp_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu ", sizeof(icp_params),'
+            'sizeof(icp_iteration), sizeof(icp_stats), sizeof(icp_result), sizeof(icp_octree_info));'
+            'printf("%zu %zu\\n", sizeof(icp_las_header), sizeof(icp_las_points));return 0;}\n')
     import tempfile
     with tempfile.TemporaryDirectory() as td:
         src = os.path.join(td, "s.c")
@@ -58,7 +59,29 @@ def test_struct_layouts_match_header_sizes():
         subprocess.check_call([cc, "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     assert sizes == [C.sizeof(lib.IcpParams), C.sizeof(lib.IcpIteration), C.sizeof(lib.IcpStats), C.sizeof(lib.IcpResult),
-                     C.sizeof(lib.IcpOctreeInfo)]
+                     C.sizeof(lib.IcpOctreeInfo), C.sizeof(lib.IcpLasHeader), C.sizeof(lib.IcpLasPoints)]
+
+
+def test_host_only_entry_points_work_without_a_device(tmp_path):
+    """icp_las_parse_header and icp_save_transformation are host-side framing: no handle, no GPU."""
+    import numpy as np
+    import io_cases
+    from iterativeclosestpoint_b200 import cloudio
+    from oracle.binding import OracleIO
+    img = io_cases.foreign_las_image()
+    h = cloudio.las_parse_header(img[:227])
+    assert (h.offset_to_data, h.n_points, h.record_length) == (375, 700, 34)
+    assert list(h.scale) == [0.01, 0.01, 0.001] and list(h.offset) == [500_000.0, 4_100_000.0, -12.5]
+    bad = img.copy(); bad[0] = ord("X")
+    with pytest.raises(_lib().IcpError):
+        cloudio.las_parse_header(bad[:227])
+    T = io_cases.transform_case(1)
+    p = str(tmp_path / "t.txt")
+    assert cloudio.saveTransformation(T[:3, :3], T[:3, 3], p, [T])
+    assert open(p, "rb").read() == OracleIO().transformation_text(T[:3, :3], T[:3, 3], [T])
+    g = np.load(os.path.join(ROOT, "tests", "golden", "io_transformation_text.npz"))
+    assert cloudio.saveTransformation(io_cases.transform_case(0)[:3, :3], io_cases.transform_case(0)[:3, 3], p, None)
+    assert open(p, "rb").read() == g["text_0"].tobytes()
 
 
 def test_default_params_are_the_reference_defaults():
