@@ -105,6 +105,7 @@ static int ensure_run_buffers(Ctx* c, int64_t n) {
     ICPB_TRY(devbuf_reserve(c, c->dist, (size_t)n * sizeof(double)));
     ICPB_TRY(devbuf_reserve(c, c->mask, (size_t)n));
     ICPB_TRY(devbuf_reserve(c, c->node_io, (size_t)n * sizeof(uint32_t)));
+    ICPB_TRY(devbuf_reserve(c, c->lb, (size_t)n * sizeof(float)));
     const size_t nbA = (size_t)std::max<int64_t>(stat_a_blocks(c, n), (n + 255) / 256 / 4) + 1024;
     ICPB_TRY(devbuf_reserve(c, c->part_a, nbA * sizeof(StatA)));
     ICPB_TRY(devbuf_reserve(c, c->part_b, (size_t)(stage_b_blocks(c, n) + 8) * STATB_DOUBLES * sizeof(double)));
@@ -286,6 +287,8 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     c->prev_valid = false;
     if (c->opt_nn_mode == 2 && !resume)  // per-tile start nodes: the root until a tile has searched once
         ICPB_CUDA(c, cudaMemsetAsync(c->node_io.p, 0, (size_t)((n + 31) / 32) * sizeof(uint32_t), c->stream));
+    if (c->opt_nn_mode == 4)  // temporal bounds belong to one run: the source moves between runs
+        ICPB_CUDA(c, cudaMemsetAsync(c->lb.p, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(float), c->stream));
     ICPB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     for (int iter = 0; iter < P.max_iterations; ++iter) {
         if (variant == ICP_VARIANT_ENGINE && stop_flag && *stop_flag) {  // icpengine.cpp:160-164
@@ -306,6 +309,7 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         L.prev_pos = ((iter > 0 || resume) && c->opt_nn_mode >= 1) ? (uint32_t*)c->pos.p : nullptr;
         L.node_io = (c->opt_nn_mode == 1) ? (uint32_t*)c->node_io.p : nullptr;
         L.tile_node = (c->opt_nn_mode == 2) ? (uint32_t*)c->node_io.p : nullptr;
+        L.lb_io = (float*)c->lb.p;
         L.part_a = nullptr;
         L.state = c->d_state;
         L.apply_pending = 1;
@@ -512,7 +516,7 @@ void icp_destroy(icp_handle h) {
     c->workers.clear();
     octree_free(c);
     DevBuf* bufs[] = {&c->tgt_raw, &c->sx, &c->sy, &c->sz, &c->sperm, &c->pos, &c->dist, &c->mask, &c->part_a, &c->part_b,
-                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt};
+                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt, &c->lb};
     for (DevBuf* b : bufs) devbuf_free(*b);
     if (c->pin_a.p) cudaFreeHost(c->pin_a.p);
     if (c->pin_b.p) cudaFreeHost(c->pin_b.p);
@@ -587,6 +591,7 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     else if (!strcmp(key, "terminal_pts")) c->opt_terminal_pts = std::min(std::max((int)value, 1), 1024);
     else if (!strcmp(key, "search_leaf")) c->opt_search_leaf = std::min(std::max((int)value, 1), 1024);
     else if (!strcmp(key, "order_queries")) c->opt_order_queries = value != 0.0;
+    else if (!strcmp(key, "temporal_skip")) c->opt_temporal_skip = value != 0.0;
     else if (!strcmp(key, "write_mask")) c->opt_write_mask = value != 0.0;
     else {
         c->err = std::string("unknown option ") + key;
@@ -620,7 +625,7 @@ int icp_nn_tile_counters(icp_handle h, int64_t* per_thread_lanes, int64_t* candi
     if (getenv("ICP_B200_DEBUG_COUNTERS")) {
         unsigned long long w[8];
         ICPB_CUDA(c, cudaMemcpy(w, c->d_counters, sizeof w, cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[icp_b200] tile counters: slow_lanes=%llu candidates=%llu rounds=%llu passes=%llu nodes=%llu start_steps=%llu\n", w[2], w[3],
+        fprintf(stderr, "[icp_b200] tile counters: slow_lanes=%llu candidates=%llu rounds(mode 4: scan items)=%llu passes(mode 4: matches kept without a search)=%llu nodes=%llu start_steps=%llu\n", w[2], w[3],
                 w[4], w[5], w[6], w[7]);
     }
     if (reset) ICPB_CUDA(c, cudaMemset(c->d_counters + 2, 0, 6 * sizeof(unsigned long long)));

@@ -77,7 +77,9 @@ struct Ctx {
     DevBuf sx, sy, sz, sperm;  // SoA coordinates + original index of each internal slot
     int64_t n_src = 0;
     DevBuf pos, dist, mask;    // per-query NN result (sorted target position), distance, inlier mask
-    DevBuf node_io;            // per-query leaf of the last match (temporal start of the next search)
+    DevBuf node_io;            // per-query leaf of the last match (temporal start of the next search); mode 4: the work list
+    DevBuf lb;                 // mode 4: per-query lower bound on the distance to every non-matched target point (float)
+    bool opt_temporal_skip = true;  // mode 4: keep a match without searching when that bound proves it
     DevBuf part_a, part_b;     // per-block partials
     DevBuf scratch0, scratch1, scratch2, scratch3, scratch_src;
     DevBuf las_src, las_tgt;   // raw LAS point records of icp_register_las, decoded on the device (cloudio.cu)
@@ -150,6 +152,7 @@ struct NNLaunch {
     const uint32_t* prev_pos;  // last iteration's match per query, seeds the search (may be null)
     uint32_t* node_io;         // in: node the previous search started from; out: this one's (may be null)
     uint32_t* tile_node = nullptr;  // mode 2: per-tile start node of the last search (may be null)
+    float* lb_io = nullptr;         // mode 4: temporal bounds, valid for the positions the queries have on entry (may be null)
     StatA* part_a;         // per-block partial (may be null: no statistics)
     const LoopState* state;  // may be null (stateless query)
     int apply_pending;     // read state->have_T / T_pending and transform on load

@@ -103,17 +103,12 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
     bool fell_back = false;
 
     if (A.worklist) {
-        // second half of mode 4: the queries nn_group_kernel could not settle (already moved, matches untouched)
-        const long long cnt = (long long)*A.work_count;
-        unsigned long long fb = 0, ok = 0;
-        for (long long t = i; t < cnt; t += (long long)gridDim.x * NN_THREADS) {
-            bool f = false;
-            nn_one_query(A, (long long)A.worklist[t], true, stk, st, f);
-            fb += f ? 1ull : 0ull;
-            ok += f ? 0ull : 1ull;
+        // second half of mode 4: the queries nn_group_kernel could not settle (already moved, matches untouched).
+        // One query per thread, as many blocks as the list could need at most; the surplus exits at once.
+        if (i < (long long)*A.work_count) {
+            nn_one_query(A, (long long)A.worklist[i], true, stk, st, fell_back);
+            if (A.counters) atomicAdd(&A.counters[fell_back ? 1 : 0], 1ull);
         }
-        if (A.counters && fb) atomicAdd(&A.counters[1], fb);
-        if (A.counters && ok) atomicAdd(&A.counters[0], ok);
         return;
     }
     const bool active = i < A.n;
@@ -162,6 +157,7 @@ int nn_launch(Ctx* c, const NNLaunch& L) {
         A.goff[k] = c->fast.goff[k];
         for (int a = 0; a < 3; ++a) A.gdim[k][a] = c->fast.gdim[k][a];
         A.ginv[k] = (k < c->fast.glev_n) ? (double)(1ll << (c->fast.glev_min + k)) / c->fast.cube : 0.0;
+        A.gedge[k] = (k < c->fast.glev_n) ? c->fast.cube / (double)(1ll << (c->fast.glev_min + k)) : 0.0;
     }
     for (int a = 0; a < 3; ++a) A.gorg[a] = c->fast.root_lo[a];
     // finest cell * 2^-20 >> any rounding of the bisection boundaries
@@ -185,6 +181,7 @@ int nn_launch(Ctx* c, const NNLaunch& L) {
     A.terminal_pts = c->opt_terminal_pts;
     A.worklist = nullptr;
     A.work_count = nullptr;
+    A.lb_io = (L.mode == 4 && c->opt_temporal_skip) ? L.lb_io : nullptr;
     if (L.mode == 2) return nn_tile_launch(c, A);
     if (L.mode == 4) {
         // the balanced kernel settles what it can; the per-thread kernel (cell walk, then climb / literal) takes the rest
@@ -198,8 +195,7 @@ int nn_launch(Ctx* c, const NNLaunch& L) {
             if (c->opt_walk_bias == -100) A.gbias = -2;
             A.apply_pending = 0;
             A.node_io = nullptr;
-            const int blocks = std::min(nn_grid_blocks(L.n), c->sm_count * 7);
-            nn_kernel<<<blocks, NN_THREADS, 0, c->stream>>>(A);
+            nn_kernel<<<nn_grid_blocks(L.n), NN_THREADS, 0, c->stream>>>(A);
             c->launches++;
             ICPB_CUDA(c, cudaGetLastError());
             return ICP_OK;

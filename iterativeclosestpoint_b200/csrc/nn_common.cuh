@@ -45,6 +45,9 @@ struct NNArgs {
     int mode;                  // 0: literal traversal from the root; 1: per-thread, climb from the last leaf; 2: warp tiles;
                                // 3: per-thread, entry through the grid cells the search ball touches;
                                // 4: as 3, the candidate scan balanced over the warp (nn_group.cu)
+    float* lb_io;              // mode 4: per query, a lower bound on the distance to every target point other than its match
+                               // (rounded down; 0 = unknown) -- lets a later iteration keep the match without a search
+    double gedge[4];           // cell edge per pyramid level
     uint32_t* worklist;        // mode 4: queries the balanced kernel hands to the per-thread kernel ...
     unsigned int* work_count;  // ... and how many; the per-thread kernel runs over that list when worklist != null
     double init_best;

@@ -447,3 +447,25 @@ def test_full_size_config3_sample_parity_and_properties(handle, oracle):
     assert np.array_equal(idx2[sample], otree.find_nearest(moved[sample], nthreads=oracle.hw_threads()))
     # inlier counts of the three iterations against the oracle's statistics on the GPU's own correspondences
     assert all(h.validPoints + h.outlierPoints == len(src) for h in res.iterationHistory)
+
+
+def test_balanced_walk_with_temporal_skip_is_bit_identical_to_the_per_thread_walk(handle):
+    """nn_mode 4 keeps a match without searching when its recorded lower bound proves it (nn_group.cu).  The NN indices and
+    distances feed order-deterministic reductions, so a whole run must reproduce mode 3's transforms bit for bit."""
+    src, tgt = synth.make_pair(300_000, 2, "primary")
+    runs = {}
+    for name, mode, skip in (("walk", 3, 0), ("group", 4, 0), ("group+skip", 4, 1)):
+        handle.set_option("nn_mode", mode)
+        handle.set_option("temporal_skip", skip)
+        handle.set_params(ICPParameters(maxIterations=40, tolerance=1e-15))
+        work = src.copy()
+        runs[name] = (handle.register(work, tgt), work)
+    base, base_src = runs["walk"]
+    assert base.loopIterations >= 13
+    for name in ("group", "group+skip"):
+        got, moved = runs[name]
+        assert got.totalIterations == base.totalIterations and got.loopIterations == base.loopIterations
+        assert np.array_equal(got.cumulativeT, base.cumulativeT), name
+        assert [h.validPoints for h in got.iterationHistory] == [h.validPoints for h in base.iterationHistory]
+        assert [h.rmse for h in got.iterationHistory] == [h.rmse for h in base.iterationHistory]
+        assert np.array_equal(moved, base_src)

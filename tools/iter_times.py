@@ -10,7 +10,7 @@ for regime in (sys.argv[2:] or ['primary','stress']):
         h=Handle(0); h.set_option('nn_mode',mode); h.set_option('count', float(os.environ.get('ICP_COUNT','0')))
         for kv in os.environ.get('ICP_OPTS','').split(','):
             if kv: h.set_option(kv.split('=')[0], float(kv.split('=')[1]))
-        h.set_params(ICPParameters(maxIterations=16))
+        h.set_params(ICPParameters(maxIterations=int(os.environ.get("ICP_ITERS","16"))))
         w=src.copy(); t0=time.time(); r=h.register(w,tgt); dt=time.time()-t0
         print(f'{regime} m={m} mode={mode} iters={r.loopIterations} wall={dt:.3f}s timings={ {k:round(v,2) for k,v in r.timings_ms.items()} }')
         print('   nn_ms:',[round(i.nnMs,2) for i in r.iterationHistory])
