@@ -192,7 +192,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--nn-mode", type=int, default=4)
+    ap.add_argument("--nn-mode", type=int, default=6)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

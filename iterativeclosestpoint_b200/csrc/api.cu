@@ -29,7 +29,7 @@ int pairs_b_launch(Ctx* c, const double* a_xyz, const double* b_xyz, int64_t n, 
 int solve_launch(Ctx* c, const double* rank_parts, int n_ranks);
 int bestfit_launch(Ctx* c, const double* b17, const double* a0, const double* b0, double* T_out);
 int solve_from_H_launch(Ctx* c, const double* in15, double* out37);
-int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n);
+int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n, float* lb = nullptr);
 int unsort_results_launch(Ctx* c, const uint32_t* pos, const double* dist, const uint32_t* perm, int64_t n, int32_t* idx_out,
                           double* dist_out);
 int aos_to_soa_launch(Ctx* c, const double* xyz, int64_t n, double* sx, double* sy, double* sz);
@@ -106,6 +106,10 @@ static int ensure_run_buffers(Ctx* c, int64_t n) {
     ICPB_TRY(devbuf_reserve(c, c->mask, (size_t)n));
     ICPB_TRY(devbuf_reserve(c, c->node_io, (size_t)n * sizeof(uint32_t)));
     ICPB_TRY(devbuf_reserve(c, c->lb, (size_t)n * sizeof(float)));
+    if (c->opt_nn_mode >= 5) {
+        ICPB_TRY(devbuf_reserve(c, c->cand, (size_t)n * sizeof(uint4)));
+        ICPB_TRY(devbuf_reserve(c, c->work2, (size_t)n * sizeof(uint32_t)));
+    }
     const size_t nbA = (size_t)std::max<int64_t>(stat_a_blocks(c, n), (n + 255) / 256 / 4) + 1024;
     ICPB_TRY(devbuf_reserve(c, c->part_a, nbA * sizeof(StatA)));
     ICPB_TRY(devbuf_reserve(c, c->part_b, (size_t)(stage_b_blocks(c, n) + 8) * STATB_DOUBLES * sizeof(double)));
@@ -289,6 +293,19 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         ICPB_CUDA(c, cudaMemsetAsync(c->node_io.p, 0, (size_t)((n + 31) / 32) * sizeof(uint32_t), c->stream));
     if (c->opt_nn_mode == 4)  // temporal bounds belong to one run: the source moves between runs
         ICPB_CUDA(c, cudaMemsetAsync(c->lb.p, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(float), c->stream));
+    // modes 5 / 6: candidates and bounds survive between runs over the same resident source and tree (the loop's last
+    // transform is applied by apply_pending_launch, which shrinks the bounds by the distance each point moves)
+    const bool keep_state = c->opt_nn_mode >= 5 && resume && c->keep_valid;
+    if (c->opt_nn_mode == 5 && !keep_state) {
+        ICPB_CUDA(c, cudaMemsetAsync(c->lb.p, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(float), c->stream));
+        ICPB_CUDA(c, cudaMemsetAsync(c->cand.p, 0xFF, (size_t)std::max<int64_t>(n, 1) * sizeof(uint4), c->stream));
+    }
+    c->keep_valid = false;
+    // mode 6: the balanced walk while the registration still moves by a good fraction of the point spacing per iteration
+    // (few matches survive an iteration, recording bounds only costs), keep / collect once it has (nearly) converged:
+    // phase 0 walk; 1 walk that also records bounds (the hand-over iteration); 2 keep / collect
+    int phase = (c->opt_nn_mode == 6 && keep_state) ? 2 : 0;
+    double prev_rmse = (c->opt_nn_mode == 6 && resume) ? c->last_rmse : -1.0;
     ICPB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     for (int iter = 0; iter < P.max_iterations; ++iter) {
         if (variant == ICP_VARIANT_ENGINE && stop_flag && *stop_flag) {  // icpengine.cpp:160-164
@@ -310,10 +327,29 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         L.node_io = (c->opt_nn_mode == 1) ? (uint32_t*)c->node_io.p : nullptr;
         L.tile_node = (c->opt_nn_mode == 2) ? (uint32_t*)c->node_io.p : nullptr;
         L.lb_io = (float*)c->lb.p;
+        L.cand_io = (c->opt_nn_mode >= 5) ? (uint4*)c->cand.p : nullptr;
         L.part_a = nullptr;
         L.state = c->d_state;
         L.apply_pending = 1;
         L.mode = c->opt_nn_mode;
+        if (c->opt_nn_mode == 6) {
+            const double sp = c->fast.spacing;
+            const bool near = prev_rmse >= 0.0 && prev_rmse <= c->opt_keep_enter * sp;
+            const bool stay = prev_rmse >= 0.0 && prev_rmse <= c->opt_keep_exit * sp;
+            L.mode = 4;
+            if (!L.prev_pos || !c->opt_temporal_skip || !(phase == 0 ? near : stay)) {
+                phase = 0;
+                L.lb_io = nullptr;
+                L.cand_io = nullptr;
+            } else if (phase == 0) {
+                phase = 1;
+                ICPB_CUDA(c, cudaMemsetAsync(c->lb.p, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(float), c->stream));
+                ICPB_CUDA(c, cudaMemsetAsync(c->cand.p, 0xFF, (size_t)std::max<int64_t>(n, 1) * sizeof(uint4), c->stream));
+            } else {
+                phase = 2;
+                L.mode = 5;
+            }
+        }
         L.init_best = init_best;
         ICPB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
         ICPB_TRY(nn_launch(c, L));
@@ -340,14 +376,27 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         out->ms_nn_total += nn_ms;
         if (iter == 0) out->ms_nn_first = nn_ms;
         const IterRecord rec = *c->h_rec;
+        if (c->opt_count && getenv("ICP_B200_DEBUG_ITER")) {  // profiling aid: counters and work-list lengths of this iteration
+            unsigned long long w[8];
+            unsigned int wc[2];
+            cudaMemcpy(w, c->d_counters, sizeof w, cudaMemcpyDeviceToHost);
+            cudaMemcpy(wc, c->d_work_count, sizeof wc, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[icp_b200] iter %d nn %.3f ms: settled=%llu literal=%llu slow=%llu candidates=%llu items=%llu kept=%llu | list1=%u list2=%u\n",
+                    iter, nn_ms, w[0], w[1], w[2], w[3], w[4], w[5], wc[0], wc[1]);
+            cudaMemset(c->d_counters, 0, sizeof w);
+        }
+        prev_rmse = rec.rmse;
         if (!acc.consume(rec, iter, nn_ms, iter_ms, true)) break;
     }
     ICPB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
 
     c->prev_valid = out->loop_iterations > 0 && c->opt_nn_mode >= 1;
     *write_back = acc.write_back;
-    if (acc.write_back)
-        ICPB_TRY(apply_pending_launch(c, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p, n));  // the last T, if any
+    if (acc.write_back)  // the last T, if any
+        ICPB_TRY(apply_pending_launch(c, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p, n,
+                                      (c->opt_nn_mode == 5 || phase >= 1) ? (float*)c->lb.p : nullptr));
+    c->keep_valid = c->prev_valid && acc.write_back && (c->opt_nn_mode == 5 || phase >= 1) && c->opt_temporal_skip;
+    c->last_rmse = prev_rmse;
     acc.finish();
     ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
     {
@@ -496,12 +545,12 @@ int icp_create(icp_handle* out, int device_id) {
     if (cudaMalloc(&c->d_state, sizeof(LoopState)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long));
-    if (cudaMalloc(&c->d_work_count, sizeof(unsigned int)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    if (cudaMalloc(&c->d_work_count, 2 * sizeof(unsigned int)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaHostAlloc(&c->h_rec, sizeof(IterRecord), cudaHostAllocMapped) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaHostGetDevicePointer(&c->d_rec, c->h_rec, 0) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (getenv("ICP_B200_DEBUG_COUNTERS")) c->opt_count = true;
     const char* m = getenv("ICP_B200_NN_MODE");
-    if (m) c->opt_nn_mode = std::min(std::max(atoi(m), 0), 4);
+    if (m) c->opt_nn_mode = std::min(std::max(atoi(m), 0), 6);
     *out = (icp_handle)c;
     return ICP_OK;
 }
@@ -516,7 +565,7 @@ void icp_destroy(icp_handle h) {
     c->workers.clear();
     octree_free(c);
     DevBuf* bufs[] = {&c->tgt_raw, &c->sx, &c->sy, &c->sz, &c->sperm, &c->pos, &c->dist, &c->mask, &c->part_a, &c->part_b,
-                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt, &c->lb};
+                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt, &c->lb, &c->cand, &c->work2};
     for (DevBuf* b : bufs) devbuf_free(*b);
     if (c->pin_a.p) cudaFreeHost(c->pin_a.p);
     if (c->pin_b.p) cudaFreeHost(c->pin_b.p);
@@ -574,7 +623,7 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     Ctx* c = (Ctx*)h;
     if (!c || !key) return ICP_INVALID_ARGUMENT;
     if (!strcmp(key, "nn_mode")) {
-        c->opt_nn_mode = value < 0.5 ? 0 : (value < 1.5 ? 1 : (value < 2.5 ? 2 : (value < 3.5 ? 3 : 4)));
+        c->opt_nn_mode = value < 0.5 ? 0 : (value < 1.5 ? 1 : (value < 2.5 ? 2 : (value < 3.5 ? 3 : (value < 4.5 ? 4 : (value < 5.5 ? 5 : 6)))));
         c->prev_valid = false;
     }
     else if (!strcmp(key, "count")) c->opt_count = value != 0.0;
@@ -592,6 +641,12 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     else if (!strcmp(key, "search_leaf")) c->opt_search_leaf = std::min(std::max((int)value, 1), 1024);
     else if (!strcmp(key, "order_queries")) c->opt_order_queries = value != 0.0;
     else if (!strcmp(key, "temporal_skip")) c->opt_temporal_skip = value != 0.0;
+    else if (!strcmp(key, "keep_k")) { c->opt_keep_k = std::min(std::max((int)value, 1), 4); c->keep_valid = false; }
+    else if (!strcmp(key, "keep_alpha")) c->opt_keep_alpha = std::min(std::max(value, 1.0), 16.0);
+    else if (!strcmp(key, "keep_enter")) c->opt_keep_enter = std::max(value, 0.0);
+    else if (!strcmp(key, "keep_exit")) c->opt_keep_exit = std::max(value, 0.0);
+    else if (!strcmp(key, "keep_rcap")) c->opt_keep_rcap = std::min(std::max(value, 0.0), 8.0);
+    else if (!strcmp(key, "keep_bias")) c->opt_keep_bias = std::min(std::max((int)value, -4), 4);
     else if (!strcmp(key, "write_mask")) c->opt_write_mask = value != 0.0;
     else {
         c->err = std::string("unknown option ") + key;

@@ -12,6 +12,7 @@
 // point lands in exactly the reference's leaf and every box is bit-identical to the reference's.
 #include "internal.h"
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 namespace icpb {
@@ -758,6 +759,10 @@ static int build_grid(Ctx* c, DeviceOctree& t) {
     nlev = fine - base + 1;
     t.glev_n = nlev;
     t.glev_min = base;
+    {
+        const double occ = hist[32 + base] ? (double)hist[64 + base] / (double)hist[32 + base] : 1.0;
+        t.spacing = t.cube / (double)(1ll << base) / std::sqrt(std::max(occ, 1.0));
+    }
     long long total = 0;
     for (int k = 0; k < nlev; ++k) {
         long long n[3];

@@ -27,6 +27,7 @@ struct DeviceOctree {
     uint64_t* cell = nullptr;
     uint2* grid = nullptr;            // pyramid of dense entry grids, levels glev_min .. glev_min + glev_n - 1
     int glev_min = 0, glev_n = 0;
+    double spacing = 0.0;             // typical distance between neighbouring points (base cell edge / sqrt(points per occupied base cell))
     long long goff[4] = {0, 0, 0, 0};
     int gdim[4][3] = {};
     double cube = 0.0;                // edge of the cubic root
@@ -80,6 +81,16 @@ struct Ctx {
     DevBuf node_io;            // per-query leaf of the last match (temporal start of the next search); mode 4: the work list
     DevBuf lb;                 // mode 4: per-query lower bound on the distance to every non-matched target point (float)
     bool opt_temporal_skip = true;  // mode 4: keep a match without searching when that bound proves it
+    DevBuf cand;               // mode 5: per query, the K nearest target points of its last search (uint4; NONE = unused)
+    DevBuf work2;              // mode 5: second work list (queries handed to the per-thread kernel)
+    bool keep_valid = false;   // mode 5: cand / lb describe the resident source as it is now
+    int opt_keep_k = 4;        // mode 5: candidates carried per query (1..4)
+    double opt_keep_alpha = 2.0;  // mode 5: search ball = seed radius x alpha (a wider ball records a better bound)
+    int opt_keep_bias = 0;     // mode 5: pyramid level relative to 'cell >= ball box' (+1: up to three cells per axis)
+    double opt_keep_enter = 0.2;    // mode 6: the keep / collect kernels take over once the RMSE is below this fraction of the point spacing ...
+    double opt_keep_exit = 0.7;     // ... and hand back to the balanced walk above this one
+    double last_rmse = -1.0;        // RMSE of the last iteration of the last run over the resident source (-1: unknown)
+    double opt_keep_rcap = 0.4;  // mode 5: the ball is widened up to this fraction of the base-level cell edge at most
     DevBuf part_a, part_b;     // per-block partials
     DevBuf scratch0, scratch1, scratch2, scratch3, scratch_src;
     DevBuf las_src, las_tgt;   // raw LAS point records of icp_register_las, decoded on the device (cloudio.cu)
@@ -87,13 +98,14 @@ struct Ctx {
     bool prev_valid = false;         // pos / node_io hold last run's matches of the resident source against the current tree
     float last_build_ms = 0.f;
     // tuning knobs (icp_set_option)
-    int opt_nn_mode = 4;             // 0: literal traversal from the root; 1: climb; 2: warp tiles; 3: cell walk; 4: balanced cell walk
+    int opt_nn_mode = 6;             // 0: literal traversal from the root; 1: climb; 2: warp tiles; 3: cell walk; 4: balanced cell walk;
+                                     // 5: keep / collect (nn_keep.cu); 6: 4 while the registration moves, 5 once it has nearly converged
     bool opt_order_queries = true;   // Morton-order the source for traversal coherence
     bool opt_write_mask = false;     // keep the per-point inlier mask of the last iteration
     bool opt_count = false;          // maintain the NN path counters (same-address atomics: profiling / tests only)
     LoopState* d_state = nullptr;
     unsigned long long* d_counters = nullptr;  // see NNArgs::counters (4 entries)
-    unsigned int* d_work_count = nullptr;      // mode 4: length of the work list (kept in node_io) for the per-thread kernel
+    unsigned int* d_work_count = nullptr;      // mode 4/5: lengths of the two work lists (node_io, work2)
     IterRecord* h_rec = nullptr;  // pinned, device-mapped
     IterRecord* d_rec = nullptr;
 
@@ -152,7 +164,8 @@ struct NNLaunch {
     const uint32_t* prev_pos;  // last iteration's match per query, seeds the search (may be null)
     uint32_t* node_io;         // in: node the previous search started from; out: this one's (may be null)
     uint32_t* tile_node = nullptr;  // mode 2: per-tile start node of the last search (may be null)
-    float* lb_io = nullptr;         // mode 4: temporal bounds, valid for the positions the queries have on entry (may be null)
+    float* lb_io = nullptr;         // mode 4/5: temporal bounds, valid for the positions the queries have on entry (may be null)
+    uint4* cand_io = nullptr;       // mode 5: candidates of the last search per query (may be null)
     StatA* part_a;         // per-block partial (may be null: no statistics)
     const LoopState* state;  // may be null (stateless query)
     int apply_pending;     // read state->have_T / T_pending and transform on load

@@ -21,6 +21,7 @@
 //   s > best (1 + 2^-39).  If second <= best (1 + 2^-40) (exact ties, duplicates, 1-ulp near ties) the query
 //   is re-run through `dfs_literal`; otherwise the unique minimum is the reference's answer.
 #include <algorithm>
+#include <cmath>
 #include "nn_common.cuh"
 
 namespace icpb {
@@ -104,9 +105,11 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
 
     if (A.worklist) {
         // second half of mode 4: the queries nn_group_kernel could not settle (already moved, matches untouched).
-        // One query per thread, as many blocks as the list could need at most; the surplus exits at once.
-        if (i < (long long)*A.work_count) {
-            nn_one_query(A, (long long)A.worklist[i], true, stk, st, fell_back);
+        // One query per thread while the list is shorter than the grid; the surplus blocks exit at once.
+        const long long cnt = (long long)*A.work_count;
+        for (long long t = i; t < cnt; t += (long long)gridDim.x * NN_THREADS) {
+            fell_back = false;
+            nn_one_query(A, (long long)A.worklist[t], true, stk, st, fell_back);
             if (A.counters) atomicAdd(&A.counters[fell_back ? 1 : 0], 1ull);
         }
         return;
@@ -138,8 +141,12 @@ int nn_grid_blocks(int64_t n) { return (int)((n + NN_THREADS - 1) / NN_THREADS);
 
 int nn_tile_launch(Ctx* c, const NNArgs& A);   // nn_tile.cu
 int nn_group_launch(Ctx* c, const NNArgs& A);  // nn_group.cu
+int nn_group_lean_launch(Ctx* c, const NNArgs& A);  // nn_group_lean.cu
+int nn_keep_launch(Ctx* c, const NNArgs& A, int k);  // nn_keep.cu
 
-int nn_launch(Ctx* c, const NNLaunch& L) {
+int nn_launch(Ctx* c, const NNLaunch& L_in) {
+    NNLaunch L = L_in;
+    if (L.mode == 6) L.mode = 4;  // the per-iteration choice between 4 and 5 is run_loop's (api.cu); a stateless query is a plain walk
     if (L.n <= 0) return ICP_OK;
     NNArgs A;
     A.nodes = c->fast.nodes;
@@ -153,6 +160,7 @@ int nn_launch(Ctx* c, const NNLaunch& L) {
     A.gmax_cells = c->opt_walk_max_cells;
     A.gbias = c->opt_walk_bias != -100 ? c->opt_walk_bias : (L.mode == 4 ? 0 : -2);
     A.gcube = c->fast.cube;
+    A.gbias_mul = std::ldexp(1.0, -A.gbias);
     for (int k = 0; k < 4; ++k) {
         A.goff[k] = c->fast.goff[k];
         for (int a = 0; a < 3; ++a) A.gdim[k][a] = c->fast.gdim[k][a];
@@ -181,18 +189,47 @@ int nn_launch(Ctx* c, const NNLaunch& L) {
     A.terminal_pts = c->opt_terminal_pts;
     A.worklist = nullptr;
     A.work_count = nullptr;
-    A.lb_io = (L.mode == 4 && c->opt_temporal_skip) ? L.lb_io : nullptr;
+    A.lb_io = (L.mode >= 4 && c->opt_temporal_skip) ? L.lb_io : nullptr;
+    A.cand_io = nullptr;
+    A.worklist2 = nullptr;
+    A.walk_alpha = std::max(c->opt_keep_alpha, 1.0);
+    A.walk_wmul = std::ldexp(2.0, -c->opt_keep_bias);
+    A.walk_rcap = c->opt_keep_rcap * A.gedge[0];
     if (L.mode == 2) return nn_tile_launch(c, A);
-    if (L.mode == 4) {
+    const bool in_place5 = L.ox == L.sx && L.oy == L.sy && L.oz == L.sz;
+    if (L.mode == 5 && L.prev_pos && A.lb_io && L.cand_io && in_place5 && L.apply_pending && c->d_work_count && c->node_io.p && c->work2.p) {
+        // keep what last iteration's candidates and bound prove; search the rest; the per-thread kernel takes what is left
+        A.cand_io = L.cand_io;
+        A.worklist = (uint32_t*)c->node_io.p;
+        A.worklist2 = (uint32_t*)c->work2.p;
+        A.work_count = c->d_work_count;
+        ICPB_CUDA(c, cudaMemsetAsync(c->d_work_count, 0, 2 * sizeof(unsigned int), c->stream));
+        ICPB_TRY(nn_keep_launch(c, A, c->opt_keep_k));
+        A.mode = 3;
+        A.gbias = c->opt_walk_bias != -100 ? c->opt_walk_bias : -2;
+        A.gbias_mul = std::ldexp(1.0, -A.gbias);
+        A.apply_pending = 0;
+        A.node_io = nullptr;
+        A.worklist = A.worklist2;
+        A.work_count = c->d_work_count + 1;
+        nn_kernel<<<std::min(nn_grid_blocks(L.n), c->sm_count * 64), NN_THREADS, 0, c->stream>>>(A);
+        c->launches++;
+        ICPB_CUDA(c, cudaGetLastError());
+        return ICP_OK;
+    }
+    if (L.mode == 5) A.gbias = c->opt_walk_bias != -100 ? c->opt_walk_bias : 0;
+    A.gbias_mul = std::ldexp(1.0, -A.gbias);
+    if (L.mode >= 4) {
         // the balanced kernel settles what it can; the per-thread kernel (cell walk, then climb / literal) takes the rest
         const bool in_place = !L.apply_pending || (L.ox == L.sx && L.oy == L.sy && L.oz == L.sz);
         if (in_place && c->d_work_count && c->node_io.p) {
             A.worklist = (uint32_t*)c->node_io.p;
             A.work_count = c->d_work_count;
             ICPB_CUDA(c, cudaMemsetAsync(c->d_work_count, 0, sizeof(unsigned int), c->stream));
-            ICPB_TRY(nn_group_launch(c, A));
+            ICPB_TRY(A.lb_io ? nn_group_launch(c, A) : nn_group_lean_launch(c, A));
             A.mode = 3;
             if (c->opt_walk_bias == -100) A.gbias = -2;
+            A.gbias_mul = std::ldexp(1.0, -A.gbias);
             A.apply_pending = 0;
             A.node_io = nullptr;
             nn_kernel<<<nn_grid_blocks(L.n), NN_THREADS, 0, c->stream>>>(A);

@@ -48,6 +48,11 @@ struct NNArgs {
     float* lb_io;              // mode 4: per query, a lower bound on the distance to every target point other than its match
                                // (rounded down; 0 = unknown) -- lets a later iteration keep the match without a search
     double gedge[4];           // cell edge per pyramid level
+    double gbias_mul;          // 2^-gbias
+    uint4* cand_io;            // mode 5 (nn_keep.cu): the K nearest target points of the query's last search
+    uint32_t* worklist2;       // mode 5: queries handed on to the per-thread kernel (count at work_count[1])
+    double walk_alpha, walk_wmul, walk_rcap;  // mode 5: search ball = seed radius x alpha, widened up to rcap at most; level = finest
+                               // with cell edge >= ball radius x wmul
     uint32_t* worklist;        // mode 4: queries the balanced kernel hands to the per-thread kernel ...
     unsigned int* work_count;  // ... and how many; the per-thread kernel runs over that list when worklist != null
     double init_best;
@@ -338,21 +343,37 @@ __device__ __forceinline__ GridView grid_view(const NNArgs& A, int k) {
 }
 
 // finest pyramid level whose cell edge is at least w (so a box of width w meets at most 2 cells per axis), + bias
+// (a heuristic only: the callers check the number of cells the box really meets)
 __device__ __forceinline__ int grid_level_for_width(const NNArgs& A, double w, int bias) {
-    int l = A.glmin + A.gnlev - 1;
-    if (w > 0.0) {
-        const double ratio = A.gcube / w;  // floor(log2(ratio)) from the exponent field
-        const int ex = ((__double2hiint(ratio) >> 20) & 0x7FF) - 1023;
-        l = min(l, ex + bias);
-    }
-    l = max(l, A.glmin);
-    return l - A.glmin;
+    const double ws = w * A.gbias_mul;  // w / 2^bias
+    int k = A.gnlev - 1;
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+        if (k > 0 && A.gedge[k] < ws) --k;
+    return k;
 }
 
 __device__ __forceinline__ int grid_cell_index(const NNArgs& A, const GridView& V, double v, int a, int n) {
     double f = floor(dmul(dsub(v, A.gorg[a]), V.inv));
     f = fmin(fmax(f, -1.0), (double)n);
     return (int)f;
+}
+
+// cells [lo, hi] that the interval [v - e, v + e] meets along axis a, clamped to [-1, n] like grid_cell_index; one
+// subtraction and two products per axis (the roundings, ~2^-40 of a cell, are far inside the 2^-20 cell that e carries)
+__device__ __forceinline__ void grid_cell_span(const NNArgs& A, const GridView& V, double v, double e_cells, int a, int n, int& lo,
+                                               int& hi) {
+    const double f = dmul(dsub(v, A.gorg[a]), V.inv);
+    lo = (int)fmin(fmax(floor(dsub(f, e_cells)), -1.0), (double)n);
+    hi = (int)fmin(fmax(floor(dadd(f, e_cells)), -1.0), (double)n);
+}
+
+// an upper bound of sqrt(s) within 2^-17 relative, from the single-precision reciprocal square root (two instructions
+// instead of the correctly rounded double-precision sequence); for search radii only -- distances handed to the caller
+// are always dsqrt
+__device__ __forceinline__ double sqrt_upper(double s) {
+    const float a = fmaxf(__double2float_ru(s), 1e-30f);
+    return dmul((double)(a * rsqrtf(a)), 1.0 + 7.62939453125e-06);
 }
 
 __device__ __forceinline__ uint2 grid_entry(const GridView& V, int x, int y, int z) {

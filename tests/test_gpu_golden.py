@@ -48,7 +48,7 @@ def test_octree_and_nn_match_reference_vectors(handle, name, make, leaf, depth):
                 assert np.array_equal(idx, g[key]), f"{name}/{qname}/{tag}/mode{mode}"
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3, 4], ids=["climb", "tile", "walk", "group"])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5, 6], ids=["climb", "tile", "walk", "group", "keep", "auto"])
 @pytest.mark.parametrize("name,make,kw", ENGINE_RUNS, ids=[c[0] for c in ENGINE_RUNS])
 def test_engine_runs_match_reference_vectors(handle, name, make, kw, mode):
     g = load("engine_" + name)

@@ -58,7 +58,7 @@ def test_octree_structure_bit_exact(handle, oracle, name, make, leaf, depth):
     assert info.depth == int(want["depth"].max())
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4], ids=["literal", "climb", "tile", "walk", "group"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6], ids=["literal", "climb", "tile", "walk", "group", "keep", "auto"])
 @pytest.mark.parametrize("name,make,leaf,depth", TREE_CASES, ids=[c[0] for c in TREE_CASES])
 def test_nn_indices_bit_exact(handle, oracle, name, make, leaf, depth, mode):
     tgt = make()
@@ -76,7 +76,7 @@ def test_nn_indices_bit_exact(handle, oracle, name, make, leaf, depth, mode):
         assert np.array_equal(dist, d), f"{name}/{qname}: distances are not bit-identical"
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4], ids=["literal", "climb", "tile", "walk", "group"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6], ids=["literal", "climb", "tile", "walk", "group", "keep", "auto"])
 def test_nn_lattice_ties_follow_reference_traversal_order(handle, oracle, mode):
     """Exactly equidistant candidates: the winner is the first one the reference's DFS visits, not the lowest index."""
     lat = clouds.lattice_exact()
@@ -232,7 +232,7 @@ def _check_run(got, want, n_src, tol=REL_E2E):
         assert np.max(np.abs(got.finalT - want.final_t)) <= tol * max(1.0, float(np.max(np.abs(want.final_t))))
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4], ids=["literal", "climb", "tile", "walk", "group"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6], ids=["literal", "climb", "tile", "walk", "group", "keep", "auto"])
 def test_register_config1_engine(handle, oracle, mode):
     """BASELINE.json config #1: 10k-point cloud vs transformed + noised copy, 50 / 1e-6 / 3 sigma / 10 / 20."""
     src, tgt = synth.make_test_icp_pair(10000)
@@ -469,3 +469,62 @@ def test_balanced_walk_with_temporal_skip_is_bit_identical_to_the_per_thread_wal
         assert [h.validPoints for h in got.iterationHistory] == [h.validPoints for h in base.iterationHistory]
         assert [h.rmse for h in got.iterationHistory] == [h.rmse for h in base.iterationHistory]
         assert np.array_equal(moved, base_src)
+
+
+@pytest.mark.parametrize("opts", [dict(keep_k=4), dict(keep_k=1), dict(keep_k=2, keep_alpha=1.0), dict(keep_k=3, keep_bias=0),
+                                  dict(keep_k=4, keep_alpha=2.5, keep_bias=2), dict(mode=6), dict(mode=6, keep_enter=0.9, keep_exit=1.0)],
+                         ids=["k4", "k1", "k2_alpha1", "k3_bias0", "k4_wide", "auto", "auto_early"])
+def test_keep_and_search_is_bit_identical_to_the_per_thread_walk(handle, opts):
+    """nn_mode 5 (nn_keep.cu) settles a query from the K candidates and the bound its last search recorded and searches only
+    the rest.  Indices and distances feed order-deterministic reductions, so a whole run must reproduce mode 3 bit for bit,
+    for every K / ball widening / level choice; a second run over the resident source (bounds carried across runs) too."""
+    src, tgt = synth.make_pair(300_000, 2, "primary")
+    runs = {}
+    opts = dict(opts)
+    for name, mode in (("walk", 3), ("keep", opts.pop("mode", 5))):
+        handle.set_option("nn_mode", mode)
+        if mode >= 5:
+            for k, v in opts.items():
+                handle.set_option(k, v)
+        handle.octree_build(tgt, 10, 20)
+        handle.source_upload(src)
+        out = []
+        for iters in (9, 5, 30):  # three runs over the resident source: the later ones resume from the earlier ones' state
+            handle.set_params(ICPParameters(maxIterations=iters, tolerance=1e-15))
+            out.append(handle.register_resident(len(src)))
+        runs[name] = out
+    for a, b in zip(runs["walk"], runs["keep"]):
+        assert b.totalIterations == a.totalIterations and b.loopIterations == a.loopIterations
+        assert np.array_equal(b.cumulativeT, a.cumulativeT)
+        assert [h.validPoints for h in b.iterationHistory] == [h.validPoints for h in a.iterationHistory]
+        assert [h.rmse for h in b.iterationHistory] == [h.rmse for h in a.iterationHistory]
+    for k, v in dict(keep_k=4, keep_alpha=2.0, keep_bias=0, keep_enter=0.35, keep_exit=0.7).items():
+        handle.set_option(k, v)
+
+
+@pytest.mark.parametrize("case", ["lattice", "duplicates", "coincident"])
+def test_keep_and_search_on_tie_heavy_clouds_matches_the_literal_traversal(handle, case):
+    """Exact ties, duplicated and coincident points: every query the keep / search kernels cannot prove unique must end in
+    the literal traversal, so whole runs equal nn_mode 0 bit for bit."""
+    rng = np.random.default_rng(5)
+    if case == "lattice":
+        tgt = synth.make_lattice(28, 0.025, 9)
+    elif case == "duplicates":
+        base = synth.make_target(30000, 11)
+        tgt = np.ascontiguousarray(np.concatenate([base, base[rng.integers(0, len(base), 10000)]]))
+    else:
+        tgt = np.ascontiguousarray(np.concatenate([synth.make_target(4000, 12), np.tile(synth.make_target(1, 13), (300, 1))]))
+    R = synth.rotation_zyx(0.01, 0.004, -0.003)
+    src = np.ascontiguousarray((tgt - tgt.mean(0)) @ R.T + tgt.mean(0) + np.array([0.031, -0.02, 0.012]))
+    runs = {}
+    for mode in (0, 5, 6):
+        handle.set_option("nn_mode", mode)
+        handle.set_params(ICPParameters(maxIterations=12, tolerance=1e-15))
+        work = src.copy()
+        runs[mode] = (handle.register(work, tgt), work)
+    for mode in (5, 6):
+        a, b = runs[0][0], runs[mode][0]
+        assert b.loopIterations == a.loopIterations and np.array_equal(b.cumulativeT, a.cumulativeT)
+        assert [h.validPoints for h in b.iterationHistory] == [h.validPoints for h in a.iterationHistory]
+        assert [h.rmse for h in b.iterationHistory] == [h.rmse for h in a.iterationHistory]
+        assert np.array_equal(runs[0][1], runs[mode][1])

@@ -6,7 +6,7 @@ from iterativeclosestpoint_b200.engine import Handle, ICPParameters
 m=int(sys.argv[1]) if len(sys.argv)>1 else 10_000_000
 for regime in (sys.argv[2:] or ['primary','stress']):
     src,tgt=synth.make_pair(m,3,regime)
-    for mode in [int(x) for x in os.environ.get("ICP_MODES","4,3").split(",")]:
+    for mode in [int(x) for x in os.environ.get("ICP_MODES","6,4").split(",")]:
         h=Handle(0); h.set_option('nn_mode',mode); h.set_option('count', float(os.environ.get('ICP_COUNT','0')))
         for kv in os.environ.get('ICP_OPTS','').split(','):
             if kv: h.set_option(kv.split('=')[0], float(kv.split('=')[1]))
