@@ -129,6 +129,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+NN_KERNELS = {
+    0: "icpb::nn_kernel (literal traversal)", 1: "icpb::nn_kernel (climb)", 2: "icpb::nn_tile_kernel", 3: "icpb::nn_kernel (cell walk)",
+    4: "icpb::nn_group_kernel + nn_kernel over its work list",
+    5: "icpb::nn_keep_kernel + nn_collect_kernel + nn_kernel over their work lists",
+    6: "icpb::nn_group_lean_kernel + nn_kernel over its work list while the registration moves; "
+       "nn_keep_kernel + nn_collect_kernel once it has converged",
+}
+
+
 def ncu_traffic(m: int):
     """dram bytes per NN-kernel launch from the committed ncu --set full capture, if one exists for this size."""
     p = os.path.join(ROOT, "profiles", "nn_kernel_traffic.json")
@@ -329,10 +338,12 @@ def main():
             "nn_share_of_step": nn_ms / loop_ms,
             "clocks": clocks,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "icpb::nn_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": NN_KERNELS.get(args.nn_mode, "icpb::nn_kernel"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(M), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": nn_launch_ms,
-                         "note": "exact tree search is L2/latency/FP64-issue bound, not HBM bound (SURVEY.md 8(d))"},
+                         "note": "launch_ms is the whole NN stage of one iteration (the dominant kernel plus the kernels over its "
+                                 "work lists), CUDA events inside the library on its stream; exact search is L1-wavefront / issue "
+                                 "bound while the registration moves and HBM bound once it has converged (DESIGN.md 4)"},
         }
         if e2e:
             line["e2e"] = e2e
