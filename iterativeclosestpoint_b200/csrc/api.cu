@@ -634,6 +634,7 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     else if (!strcmp(key, "range_max")) c->opt_range_max = std::max((int)value, 0);
     else if (!strcmp(key, "walk_bias")) c->opt_walk_bias = (int)value;
     else if (!strcmp(key, "search_depth")) c->opt_search_depth = std::min(std::max((int)value, 0), 21);
+    else if (!strcmp(key, "grid_coarse")) c->opt_grid_coarse = std::min(std::max((int)value, 0), 3);
     else if (!strcmp(key, "grid_shift")) c->opt_grid_shift = (int)value;
     else if (!strcmp(key, "grid_max_cells")) c->opt_grid_max_cells = std::max((long long)value, 1ll);
     else if (!strcmp(key, "walk_max_cells")) c->opt_walk_max_cells = std::max((int)value, 1);
@@ -765,12 +766,12 @@ int icp_octree_get_info(icp_handle h, icp_octree_info* info) {
     info->search_nodes = f.n_nodes;
     info->search_node_bytes = f.n_nodes * (int64_t)sizeof(Node);
     info->search_depth = f.depth;
-    info->grid_base_level = f.glev_min;
+    info->grid_base_level = f.glev_min + f.gbase;
     info->grid_fine_level = f.glev_min + f.glev_n - 1;
     if (f.glev_n > 0) {
         const int k = f.glev_n - 1;
         info->grid_bytes = (f.goff[k] + (int64_t)f.gdim[k][0] * f.gdim[k][1] * f.gdim[k][2]) * (int64_t)sizeof(uint2);
-        info->grid_base_cell = f.cube / (double)(1ll << f.glev_min);
+        info->grid_base_cell = f.cube / (double)(1ll << (f.glev_min + f.gbase));
     }
     return ICP_OK;
 }

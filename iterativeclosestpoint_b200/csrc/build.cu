@@ -745,20 +745,26 @@ static int build_grid(Ctx* c, DeviceOctree& t) {
         }
         return tot;
     };
+    // entry budget: 2^28 (2 GiB) for small clouds, 64 entries per point for large ones (a 10^8-point aerial tile needs
+    // 3.2 G entries = 26 GB for the two levels its density calls for), never above grid_max_cells
+    const double budget = std::min((double)c->opt_grid_max_cells, std::max(268435456.0, 64.0 * (double)t.n_pts));
     int nlev = 1;
     for (;;) {
         nlev = fine - base + 1;
         double tot = 0.0;
         long long n[3];
         for (int k = 0; k < nlev; ++k) tot += dims(base + k, n);
-        if (tot <= (double)c->opt_grid_max_cells || fine == 0) break;
+        if (tot <= budget || fine == 0) break;
         if (fine > base) --fine; else { --fine; --base; }
     }
     base = std::max(base, 0);
     fine = std::max(fine, base);
-    nlev = fine - base + 1;
+    // coarser levels below the base one cost an eighth of it each; the pyramid holds four levels at most
+    const int coarse = std::min(std::min(std::max(c->opt_grid_coarse, 0), base), 4 - (fine - base + 1));
+    nlev = fine - base + 1 + coarse;
     t.glev_n = nlev;
-    t.glev_min = base;
+    t.glev_min = base - coarse;
+    t.gbase = coarse;
     {
         const double occ = hist[32 + base] ? (double)hist[64 + base] / (double)hist[32 + base] : 1.0;
         t.spacing = t.cube / (double)(1ll << base) / std::sqrt(std::max(occ, 1.0));

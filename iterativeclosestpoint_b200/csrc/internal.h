@@ -27,6 +27,7 @@ struct DeviceOctree {
     uint64_t* cell = nullptr;
     uint2* grid = nullptr;            // pyramid of dense entry grids, levels glev_min .. glev_min + glev_n - 1
     int glev_min = 0, glev_n = 0;
+    int gbase = 0;                    // index (within the pyramid) of the base level; the levels before it are coarser ones for wide balls
     double spacing = 0.0;             // typical distance between neighbouring points (base cell edge / sqrt(points per occupied base cell))
     long long goff[4] = {0, 0, 0, 0};
     int gdim[4][3] = {};
@@ -64,8 +65,9 @@ struct Ctx {
     int opt_search_depth = 16;       // depth cap of the search tree
     int opt_terminal_pts = 16;       // tile kernel stages subtrees up to this size whole
     int opt_grid_shift = 0;          // entry grid level relative to the median leaf depth
-    long long opt_grid_max_cells = 1ll << 28;  // entries (8 B each) over the whole pyramid
+    long long opt_grid_max_cells = 1ll << 32;  // entries (8 B each) over the whole pyramid: up to 32 GiB of the 180 GB
     int opt_grid_levels = 3;         // pyramid height (base level + finer ones)
+    int opt_grid_coarse = 1;         // levels coarser than the base one (balanced walk only: balls wider than a base cell)
     double opt_base_occupancy = 4.0; // mean points per occupied cell the base level must still have
     int opt_range_max = 64;          // inner cells up to this many points are entered as plain point ranges
     int opt_walk_bias = -100;        // cell walk: levels finer (+) or coarser (-) than 'cell >= ball box'; -100 = per mode

@@ -157,6 +157,8 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
     A.grid = c->fast.grid;
     A.glmin = c->fast.glev_min;
     A.gnlev = c->fast.glev_n;
+    A.gbase = c->fast.gbase;
+    A.gkmin = c->fast.gbase;  // the per-thread walks stay on the base level and finer; the balanced kernels may go coarser
     A.gmax_cells = c->opt_walk_max_cells;
     A.gbias = c->opt_walk_bias != -100 ? c->opt_walk_bias : (L.mode == 4 ? 0 : -2);
     A.gcube = c->fast.cube;
@@ -194,7 +196,7 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
     A.worklist2 = nullptr;
     A.walk_alpha = std::max(c->opt_keep_alpha, 1.0);
     A.walk_wmul = std::ldexp(2.0, -c->opt_keep_bias);
-    A.walk_rcap = c->opt_keep_rcap * A.gedge[0];
+    A.walk_rcap = c->opt_keep_rcap * A.gedge[A.gbase];
     if (L.mode == 2) return nn_tile_launch(c, A);
     const bool in_place5 = L.ox == L.sx && L.oy == L.sy && L.oz == L.sz;
     if (L.mode == 5 && L.prev_pos && A.lb_io && L.cand_io && in_place5 && L.apply_pending && c->d_work_count && c->node_io.p && c->work2.p) {
@@ -204,7 +206,9 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
         A.worklist2 = (uint32_t*)c->work2.p;
         A.work_count = c->d_work_count;
         ICPB_CUDA(c, cudaMemsetAsync(c->d_work_count, 0, 2 * sizeof(unsigned int), c->stream));
+        A.gkmin = 0;
         ICPB_TRY(nn_keep_launch(c, A, c->opt_keep_k));
+        A.gkmin = A.gbase;
         A.mode = 3;
         A.gbias = c->opt_walk_bias != -100 ? c->opt_walk_bias : -2;
         A.gbias_mul = std::ldexp(1.0, -A.gbias);
@@ -226,7 +230,9 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
             A.worklist = (uint32_t*)c->node_io.p;
             A.work_count = c->d_work_count;
             ICPB_CUDA(c, cudaMemsetAsync(c->d_work_count, 0, sizeof(unsigned int), c->stream));
+            A.gkmin = 0;
             ICPB_TRY(A.lb_io ? nn_group_launch(c, A) : nn_group_lean_launch(c, A));
+            A.gkmin = A.gbase;
             A.mode = 3;
             if (c->opt_walk_bias == -100) A.gbias = -2;
             A.gbias_mul = std::ldexp(1.0, -A.gbias);

@@ -19,6 +19,7 @@ struct NNArgs {
     // entry grid of the search tree (build.cu): cell -> owning node, NONE where empty
     const uint2* __restrict__ grid;    // pyramid: levels glmin .. glmin + gnlev - 1, level k at grid + goff[k]
     int glmin, gnlev, gmax_cells, gbias;
+    int gbase, gkmin;                  // pyramid index of the base level (seeds); coarsest index the walk may use
     long long goff[4];
     int gdim[4][3];
     double ginv[4];                    // 1 / cell edge per level
@@ -349,7 +350,7 @@ __device__ __forceinline__ int grid_level_for_width(const NNArgs& A, double w, i
     int k = A.gnlev - 1;
 #pragma unroll
     for (int t = 0; t < 3; ++t)
-        if (k > 0 && A.gedge[k] < ws) --k;
+        if (k > A.gkmin && A.gedge[k] < ws) --k;
     return k;
 }
 
@@ -384,7 +385,7 @@ __device__ __forceinline__ uint2 grid_entry(const GridView& V, int x, int y, int
 // (clamped into the grid, so queries outside the cloud's box get a seed too) or of a face neighbour; +inf if none.
 __device__ __forceinline__ double walk_seed(const NNArgs& A, const double qx, const double qy, const double qz) {
     double Sd = ICPB_INF;  // any real target point is a valid seed -- a closer one only makes the walk cheaper
-    const GridView V0 = grid_view(A, 0);
+    const GridView V0 = grid_view(A, A.gbase);
     int ix = grid_cell_index(A, V0, qx, 0, V0.nx), iy = grid_cell_index(A, V0, qy, 1, V0.ny), iz = grid_cell_index(A, V0, qz, 2, V0.nz);
     ix = min(max(ix, 0), V0.nx - 1);
     iy = min(max(iy, 0), V0.ny - 1);
