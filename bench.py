@@ -202,6 +202,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--nn-mode", type=int, default=6)
+    ap.add_argument("--no-regimes", action="store_true", help="skip the near-converged and stress regimes (SURVEY.md 8(d))")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -283,6 +284,30 @@ def main():
     loop_ms, nn_ms, iters = float(t[0]), float(t[1]), int(t[2])
     clocks = sampler.summary(t_wall0, t_wall1)
 
+    # ---- the other two regimes of SURVEY.md 8(d), same tree, same W + K resident iterations (reported, not the headline) ----
+    regimes = {}
+    if not args.no_regimes and args.regime == "primary" and M <= 20_000_000:
+        from iterativeclosestpoint_b200 import synth
+        for other in ("near", "stress"):
+            rot, tr = synth.regime_transform(other)
+            osrc = synth.make_source(tgt, synth.SEED_BASE + 3, rot, tr)
+            h.source_upload(np.ascontiguousarray(osrc[lo:hi]))
+            del osrc
+            if W > 0:
+                h.set_params(ICPParameters(maxIterations=W, tolerance=0.0))
+                barrier()
+                h.register_resident(M)
+            h.set_params(ICPParameters(maxIterations=K, tolerance=0.0))
+            barrier()
+            r3 = h.register_resident(M)
+            barrier()
+            t3 = torch.tensor([float(r3.timings_ms["loop"]), float(r3.timings_ms["nn_total"]), float(r3.loopIterations)],
+                              dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            l3, n3, i3 = float(t3[0]), float(t3[1]), max(int(t3[2]), 1)
+            regimes[other] = {"value": M * i3 / (l3 * 1e-3), "ms_per_step": l3 / i3, "nn_stage_ms": n3 / i3, "steps": i3}
+
     # ---- end to end through the C ABI with host buffers -------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -345,6 +370,13 @@ def main():
                                  "work lists), CUDA events inside the library on its stream; exact search is L1-wavefront / issue "
                                  "bound while the registration moves and HBM bound once it has converged (DESIGN.md 4)"},
         }
+        if regimes:
+            for k, v in regimes.items():
+                if world == 1:  # (per rank the target term of the algorithmic bytes is not compulsory traffic)
+                    v["roofline_frac"] = alg_bytes / (v["nn_stage_ms"] * 1e-3) / 1e9 / peak
+            line["regimes"] = dict(regimes, note="same metric in the other two misalignment regimes of SURVEY.md 8(d): near = yaw 0.005 deg "
+                                   "+ 5 cm (converged: the keep kernel settles every query, HBM bound), stress = yaw 5 deg + 0.5 m "
+                                   "(edge points 43 m off: the climbing tree search carries the stage)")
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
