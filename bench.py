@@ -202,6 +202,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--nn-mode", type=int, default=6)
+    ap.add_argument("--shard", default="spatial", choices=["spatial", "blocks", "range"],
+                    help="N > 1: point ranges of the spatially (Morton) ordered source, block-cyclic ranges of the caller's order "
+                         "(64 Ki points per block), or one contiguous range of the caller's order per rank")
     ap.add_argument("--no-regimes", action="store_true", help="skip the near-converged and stress regimes (SURVEY.md 8(d))")
     args = ap.parse_args()
 
@@ -244,8 +247,14 @@ def main():
     from iterativeclosestpoint_b200 import sharding
 
     src, tgt = make_workload(M, args.regime)
-    lo, hi = sharding.shard_range(M, rank, world)
-    shard = np.ascontiguousarray(src[lo:hi])
+    shard_idx = None
+    if args.shard == "spatial" and world > 1:
+        shard_idx = sharding.shard_spatial(src, rank, world)  # host-side preparation, like generating the cloud
+        ranges = None
+        shard = np.ascontiguousarray(src[shard_idx])
+    else:
+        ranges = sharding.shard_blocks(M, rank, world) if (args.shard == "blocks" and world > 1) else [sharding.shard_range(M, rank, world)]
+        shard = sharding.take_shard(src, ranges)
 
     h = Handle(local_rank)
     h.set_option("nn_mode", args.nn_mode)
@@ -291,7 +300,7 @@ def main():
         for other in ("near", "stress"):
             rot, tr = synth.regime_transform(other)
             osrc = synth.make_source(tgt, synth.SEED_BASE + 3, rot, tr)
-            h.source_upload(np.ascontiguousarray(osrc[lo:hi]))
+            h.source_upload(np.ascontiguousarray(osrc[shard_idx]) if shard_idx is not None else sharding.take_shard(osrc, ranges))
             del osrc
             if W > 0:
                 h.set_params(ICPParameters(maxIterations=W, tolerance=0.0))
@@ -339,7 +348,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        n_local = hi - lo
+        n_local = len(shard)
         # algorithmic bytes of one NN-kernel launch on this rank: 24 B query read + 24 B
         # transformed query written back (apply fused into the load) + 4 B match + 8 B distance per query,
         # the 24 B/point target once, and the node table once.
@@ -351,7 +360,7 @@ def main():
             "warmup": W, "ms_per_step": loop_ms / max(iters, 1), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "l2": "inputs larger than L2 (source + sorted target + node table >> 126 MB)"
-                       if M >= 4_000_000 else "inputs smaller than L2; no flush", "parallelism": f"source sharded x{world}, octree replicated",
+                       if M >= 4_000_000 else "inputs smaller than L2; no flush", "parallelism": f"source sharded x{world} ({'one point range per rank of the Morton-ordered source' if args.shard == 'spatial' and world > 1 else 'block-cyclic ranges of 65536 points' if args.shard == 'blocks' and world > 1 else 'one contiguous range per rank'}), octree replicated",
                        "octree": {"nodes": int(info.n_nodes), "leaves": int(info.n_leaves), "depth": int(info.depth),
                                   "build_ms": float(info.build_ms)},
                        "search": {"nodes": int(info.search_nodes), "depth": int(info.search_depth),

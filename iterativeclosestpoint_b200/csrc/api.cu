@@ -18,13 +18,13 @@ namespace icpb {
 
 // iter.cu / build.cu entry points not in internal.h
 int stat_a_blocks(Ctx* c, int64_t n);
-int stat_a_launch(Ctx* c, const double* dist, int64_t n, StatA* part, StatA* rank_slot);
+int stat_a_launch(Ctx* c, const double* dist, int64_t n, StatA* part, StatA* rank_slot, const PeerMail* pm = nullptr);
 int stage_a_reduce_launch(Ctx* c, const StatA* part, int n_part, StatA* rank_part_slot);
 int dist_from_idx_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const int32_t* idx, int64_t n,
                          uint32_t* pos_out, double* dist_out, StatA* part, int* n_part);
 int stage_b_blocks(Ctx* c, int64_t n);
 int stage_b_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const uint32_t* pos, const double* dist,
-                   int64_t n, int iter, const StatA* rank_a, uint8_t* mask_out, double* part, double* rank_b);
+                   int64_t n, int iter, const StatA* rank_a, uint8_t* mask_out, double* part, double* rank_b, const PeerMail* pm = nullptr);
 int pairs_b_launch(Ctx* c, const double* a_xyz, const double* b_xyz, int64_t n, double* part, double* out17);
 int solve_launch(Ctx* c, const double* rank_parts, int n_ranks);
 int bestfit_launch(Ctx* c, const double* b17, const double* a0, const double* b0, double* T_out);
@@ -356,14 +356,24 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         ICPB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
 
         // stage A: this rank's Chan partial of the distances; ranks exchange partials, every rank merges them in rank order
-        ICPB_TRY(stat_a_launch(c, L.dist_out, n, part_a, rank_a + c->rank));
-        if (c->n_ranks > 1)
+        PeerMail pm;
+        pm.epoch = 0u;
+        pm.n_ranks = c->n_ranks;
+        pm.rank = c->rank;
+        const bool p2p = c->n_ranks > 1 && c->p2p;
+        if (p2p) {
+            for (int r = 0; r < MAIL_RANKS; ++r) pm.peer[r] = c->peer_mail[r];
+            if (++c->mail_epoch == 0u) ++c->mail_epoch;
+            pm.epoch = c->mail_epoch;
+        }
+        ICPB_TRY(stat_a_launch(c, L.dist_out, n, part_a, rank_a + c->rank, p2p ? &pm : nullptr));
+        if (c->n_ranks > 1 && !p2p)
             ICPB_NCCL(c, c->nccl->AllGather(rank_a + c->rank, rank_a, sizeof(StatA) / sizeof(double), ncclFloat64,
                                             (ncclComm_t)c->comm, c->stream));
         // stage B (+ the solve on a single rank)
         ICPB_TRY(stage_b_launch(c, L.sx, L.sy, L.sz, L.pos_out, L.dist_out, n, iter, rank_a,
-                                c->opt_write_mask ? (uint8_t*)c->mask.p : nullptr, part_b, rank_b));
-        if (c->n_ranks > 1) {
+                                c->opt_write_mask ? (uint8_t*)c->mask.p : nullptr, part_b, rank_b, p2p ? &pm : nullptr));
+        if (c->n_ranks > 1 && !p2p) {
             ICPB_NCCL(c, c->nccl->AllGather(rank_b + (size_t)c->rank * STATB_DOUBLES, rank_b, STATB_DOUBLES, ncclFloat64,
                                             (ncclComm_t)c->comm, c->stream));
             ICPB_TRY(solve_launch(c, rank_b, c->n_ranks));
@@ -1021,6 +1031,71 @@ int icp_comm_unique_id(icp_handle h, void* unique_id_128) {
     return ICP_OK;
 }
 
+static void mailbox_close(Ctx* c) {
+    for (int r = 0; r < MAIL_RANKS; ++r) {
+        if (c->peer_mail[r] && c->peer_mail[r] != c->mail) cudaIpcCloseMemHandle(c->peer_mail[r]);
+        c->peer_mail[r] = nullptr;
+    }
+    if (c->mail) cudaFree(c->mail);
+    c->mail = nullptr;
+    c->p2p = false;
+}
+
+// One mailbox per rank, opened by every peer through CUDA IPC; the 64-byte handles travel through the NCCL communicator that
+// was just created.  Every rank then reports whether it could open all of them: the mailboxes are used only if all could
+// (otherwise every rank keeps the two NCCL all-gathers per iteration).
+static int mailbox_open(Ctx* c, NcclApi* a) {
+    mailbox_close(c);
+    const int n = c->n_ranks;
+    ICPB_CUDA(c, cudaMalloc(&c->mail, sizeof(Mailbox)));
+    ICPB_CUDA(c, cudaMemset(c->mail, 0, sizeof(Mailbox)));
+    c->mail_epoch = 0u;
+    cudaIpcMemHandle_t mine;
+    bool ok = cudaIpcGetMemHandle(&mine, c->mail) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        std::memset(&mine, 0, sizeof mine);
+    }
+    unsigned char* d_h = nullptr;
+    ICPB_CUDA(c, cudaMalloc(&d_h, (size_t)n * sizeof mine + (size_t)n));
+    ICPB_CUDA(c, cudaMemcpyAsync(d_h + (size_t)c->rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+    ICPB_NCCL(c, a->AllGather(d_h + (size_t)c->rank * sizeof mine, d_h, sizeof mine, ncclUint8, (ncclComm_t)c->comm, c->stream));
+    std::vector<cudaIpcMemHandle_t> all(n);
+    ICPB_CUDA(c, cudaMemcpyAsync(all.data(), d_h, (size_t)n * sizeof mine, cudaMemcpyDeviceToHost, c->stream));
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < n && ok; ++r) {
+        if (r == c->rank) {
+            c->peer_mail[r] = c->mail;
+            continue;
+        }
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = false;
+        } else {
+            c->peer_mail[r] = (Mailbox*)p;
+        }
+    }
+    // agree: one byte per rank
+    unsigned char* d_ok = d_h + (size_t)n * sizeof mine;
+    const unsigned char flag = ok ? 1 : 0;
+    ICPB_CUDA(c, cudaMemcpyAsync(d_ok + c->rank, &flag, 1, cudaMemcpyHostToDevice, c->stream));
+    ICPB_NCCL(c, a->AllGather(d_ok + c->rank, d_ok, 1, ncclUint8, (ncclComm_t)c->comm, c->stream));
+    std::vector<unsigned char> oks(n);
+    ICPB_CUDA(c, cudaMemcpyAsync(oks.data(), d_ok, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_h);
+    bool all_ok = true;
+    for (int r = 0; r < n; ++r) all_ok = all_ok && oks[r] != 0;
+    if (!all_ok) {
+        log_msg(c, "peer mailboxes unavailable on some rank: per-iteration records go through NCCL all-gathers");
+        mailbox_close(c);
+        return ICP_OK;
+    }
+    c->p2p = true;
+    return ICP_OK;
+}
+
 int icp_comm_init(icp_handle h, int rank, int n_ranks, const void* unique_id_128) {
     Ctx* c = (Ctx*)h;
     if (!c || !unique_id_128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return ICP_INVALID_ARGUMENT;
@@ -1034,12 +1109,15 @@ int icp_comm_init(icp_handle h, int rank, int n_ranks, const void* unique_id_128
     c->comm = comm;
     c->rank = rank;
     c->n_ranks = n_ranks;
+    c->p2p = false;
+    if (n_ranks > 1 && n_ranks <= MAIL_RANKS && !getenv("ICP_B200_NO_P2P")) ICPB_TRY(mailbox_open(c, a));
     return ICP_OK;
 }
 
 int icp_comm_destroy(icp_handle h) {
     Ctx* c = (Ctx*)h;
     if (!c) return ICP_INVALID_ARGUMENT;
+    mailbox_close(c);
     if (c->comm && c->nccl) c->nccl->CommDestroy((ncclComm_t)c->comm);
     c->comm = nullptr;
     c->rank = 0;

@@ -106,6 +106,49 @@ struct LoopState {
 };
 
 // Host-visible record written once per iteration by the solve step.
+// Peer-to-peer exchange of the two per-iteration records (multi-GPU, one process per GPU): every rank owns one Mailbox in
+// device memory, opened by all its peers through CUDA IPC.  The producing kernel's last block stores its record straight
+// into every peer's mailbox over NVLink and then the epoch into that peer's flag; consumers spin on their OWN mailbox's
+// flags (local memory) until every rank's epoch has arrived.  No collective launch, no host round trip.
+constexpr int MAIL_RANKS = 8;
+struct Mailbox {
+    unsigned int flag_a[MAIL_RANKS];  // epoch of the stage-A record last written by rank r
+    unsigned int flag_b[MAIL_RANKS];  // ... stage-B record
+    StatA a[MAIL_RANKS];
+    double b[MAIL_RANKS][STATB_DOUBLES];
+};
+struct PeerMail {
+    Mailbox* peer[MAIL_RANKS];  // peer[r] = rank r's mailbox as mapped into this process (peer[rank] = the own one)
+    int n_ranks, rank;
+    unsigned int epoch;         // > 0: exchange through the mailboxes; 0: records are gathered by the caller (NCCL) or single rank
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// wait until every rank's epoch in `flags` has reached `epoch` (wrap-safe).  A peer that died would leave this kernel spinning
+// for ever, so the wait gives up after ~4 s of GPU time and reports it (the callers then let the run fail cleanly).
+__device__ __forceinline__ bool mail_wait(const unsigned int* flags, int n_ranks, unsigned int epoch) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int r = 0; r < n_ranks; ++r) {
+        unsigned int spins = 0;
+        while ((int)(ld_acquire_sys(flags + r) - epoch) < 0) {
+            if ((++spins & 0xFFFFu) == 0u) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 4000000000ull) return false;
+            }
+        }
+    }
+    return true;
+}
+
 struct IterRecord {
     int iteration;
     int valid_points;

@@ -106,6 +106,12 @@ struct Ctx {
     bool opt_write_mask = false;     // keep the per-point inlier mask of the last iteration
     bool opt_count = false;          // maintain the NN path counters (same-address atomics: profiling / tests only)
     LoopState* d_state = nullptr;
+    // peer-to-peer exchange of the per-iteration records (common.cuh: Mailbox); falls back to the two NCCL all-gathers when
+    // the mailboxes cannot be opened on every rank
+    Mailbox* mail = nullptr;
+    Mailbox* peer_mail[MAIL_RANKS] = {};
+    bool p2p = false;
+    unsigned int mail_epoch = 0;
     unsigned long long* d_counters = nullptr;  // see NNArgs::counters (4 entries)
     unsigned int* d_work_count = nullptr;      // mode 4/5: lengths of the two work lists (node_io, work2)
     IterRecord* h_rec = nullptr;  // pinned, device-mapped

@@ -57,7 +57,7 @@ __device__ __forceinline__ StatA stat_block_merge(StatA acc, StatA* sm /* RED_TH
 
 __global__ void __launch_bounds__(RED_THREADS) stat_a_kernel(const double* __restrict__ dist, int64_t n,
                                                              StatA* __restrict__ part, unsigned int* __restrict__ ticket,
-                                                             StatA* __restrict__ rank_slot) {
+                                                             StatA* __restrict__ rank_slot, const PeerMail pm) {
     __shared__ StatA sm[RED_THREADS];
     __shared__ bool is_last;
     // block-contiguous chunk, thread-strided inside it (coalesced, fixed assignment)
@@ -84,14 +84,25 @@ __global__ void __launch_bounds__(RED_THREADS) stat_a_kernel(const double* __res
         *rank_slot = all;
         *ticket = 0u;
     }
+    if (pm.epoch && threadIdx.x < pm.n_ranks) {
+        // this rank's record into every rank's mailbox (its own included), then the epoch: one thread per destination
+        Mailbox* m = pm.peer[threadIdx.x];
+        m->a[pm.rank] = all;
+        __threadfence_system();
+        st_release_sys(&m->flag_a[pm.rank], pm.epoch);
+    }
 }
 
 int stat_a_blocks(Ctx* c, int64_t n) {
     return (int)std::max<int64_t>(1, std::min<int64_t>((n + RED_THREADS - 1) / RED_THREADS, (int64_t)c->sm_count * 8));
 }
 
-int stat_a_launch(Ctx* c, const double* dist, int64_t n, StatA* part, StatA* rank_slot) {
-    stat_a_kernel<<<stat_a_blocks(c, n), RED_THREADS, 0, c->stream>>>(dist, n, part, &c->d_state->ticket_a, rank_slot);
+int stat_a_launch(Ctx* c, const double* dist, int64_t n, StatA* part, StatA* rank_slot, const PeerMail* pm) {
+    PeerMail none;
+    none.epoch = 0u;
+    none.n_ranks = 1;
+    none.rank = 0;
+    stat_a_kernel<<<stat_a_blocks(c, n), RED_THREADS, 0, c->stream>>>(dist, n, part, &c->d_state->ticket_a, rank_slot, pm ? *pm : none);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
     return ICP_OK;
@@ -233,15 +244,25 @@ __global__ void __launch_bounds__(RED_THREADS, 2) stage_b_kernel(const double* _
                                                               const TPoint* __restrict__ pts, LoopState* __restrict__ st,
                                                               const StatA* __restrict__ rank_a, int n_ranks, int rank, int iter,
                                                               uint8_t* __restrict__ mask_out, double* __restrict__ part,
-                                                              double* __restrict__ rank_b, IterRecord* __restrict__ rec) {
+                                                              double* __restrict__ rank_b, IterRecord* __restrict__ rec,
+                                                              const PeerMail pm) {
     __shared__ double s_thr;
+    __shared__ double s_rb[MAIL_RANKS * STATB_DOUBLES];
     __shared__ double sm_red[RED_THREADS];
     __shared__ bool is_last;
     StatA a_all;
     double mean = 0.0, sd = 0.0;
     if (threadIdx.x == 0) {
         double thr;
-        stat_a_finalize(st, rank_a, n_ranks, iter, a_all, mean, sd, thr);
+        if (pm.epoch) {
+            // the stage-A records arrive in this rank's own mailbox; read them past the caches once every epoch is in
+            const Mailbox* own = pm.peer[pm.rank];
+            const bool arrived = mail_wait(own->flag_a, n_ranks, pm.epoch);
+            stat_a_finalize(st, own->a, n_ranks, iter, a_all, mean, sd, thr);  // (loads past L1: ld.global.cg)
+            if (!arrived) thr = __longlong_as_double(0x7FF8000000000000LL);  // a peer is gone: no inliers, the run ends
+        } else {
+            stat_a_finalize(st, rank_a, n_ranks, iter, a_all, mean, sd, thr);
+        }
         s_thr = thr;
     }
     __syncthreads();
@@ -308,6 +329,26 @@ __global__ void __launch_bounds__(RED_THREADS, 2) stage_b_kernel(const double* _
             solve_step(st, rank_b, 1, rec);
         }
     }
+    if (pm.epoch) {
+        // this rank's 17 sums into every mailbox, then the epoch; then wait for everyone's and solve right here --
+        // every rank sums the records in rank order with the same arithmetic, so all ranks hold the same transform
+        __syncthreads();
+        __threadfence();
+        const double* mine = rank_b + (int64_t)rank * STATB_DOUBLES;
+        for (int t = threadIdx.x; t < n_ranks * STATB_DOUBLES; t += RED_THREADS)
+            pm.peer[t / STATB_DOUBLES]->b[rank][t % STATB_DOUBLES] = __ldcg(mine + t % STATB_DOUBLES);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < n_ranks) st_release_sys(&pm.peer[threadIdx.x]->flag_b[rank], pm.epoch);
+        const Mailbox* own = pm.peer[rank];
+        __shared__ bool s_arrived;
+        if (threadIdx.x == 0) s_arrived = mail_wait(own->flag_b, n_ranks, pm.epoch);
+        __syncthreads();
+        for (int t = threadIdx.x; t < n_ranks * STATB_DOUBLES; t += RED_THREADS)
+            s_rb[t] = s_arrived ? __ldcg(&own->b[t / STATB_DOUBLES][t % STATB_DOUBLES]) : 0.0;  // nothing => fewer than 3 inliers
+        __syncthreads();
+        if (threadIdx.x == 0) solve_step(st, s_rb, n_ranks, rec);
+    }
 }
 
 // explicit pairs (best-fit stage API): all pairs are inliers, pivots = first pair
@@ -359,10 +400,14 @@ int stage_b_blocks(Ctx* c, int64_t n) {
 }
 
 int stage_b_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const uint32_t* pos, const double* dist,
-                   int64_t n, int iter, const StatA* rank_a, uint8_t* mask_out, double* part, double* rank_b) {
+                   int64_t n, int iter, const StatA* rank_a, uint8_t* mask_out, double* part, double* rank_b, const PeerMail* pm) {
+    PeerMail none;
+    none.epoch = 0u;
+    none.n_ranks = 1;
+    none.rank = 0;
     const int blocks = stage_b_blocks(c, n);
     stage_b_kernel<<<blocks, RED_THREADS, 0, c->stream>>>(sx, sy, sz, pos, dist, n, c->fast.pts, c->d_state, rank_a, c->n_ranks,
-                                                          c->rank, iter, mask_out, part, rank_b, c->d_rec);
+                                                          c->rank, iter, mask_out, part, rank_b, c->d_rec, pm ? *pm : none);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
     return ICP_OK;

@@ -229,8 +229,8 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
         if (in_place && c->d_work_count && c->node_io.p) {
             A.worklist = (uint32_t*)c->node_io.p;
             A.work_count = c->d_work_count;
-            ICPB_CUDA(c, cudaMemsetAsync(c->d_work_count, 0, sizeof(unsigned int), c->stream));
             A.gkmin = 0;
+            ICPB_CUDA(c, cudaMemsetAsync(c->d_work_count, 0, sizeof(unsigned int), c->stream));
             ICPB_TRY(A.lb_io ? nn_group_launch(c, A) : nn_group_lean_launch(c, A));
             A.gkmin = A.gbase;
             A.mode = 3;

@@ -19,6 +19,65 @@ def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     return (n * rank) // world, (n * (rank + 1)) // world
 
 
+def shard_blocks(n: int, rank: int, world: int, block: int = 65536) -> list[tuple[int, int]]:
+    """Block-cyclic point ranges: [0, n) cut into contiguous blocks of `block` points, dealt round-robin to the ranks.
+    Still sharding by point range, but a cloud whose caller order is spatially sorted (scan strips, or the synthetic
+    scene's terrain-then-boxes order) no longer hands one rank all the hard queries: the per-iteration time is the
+    maximum over ranks.  The ranges of all ranks tile [0, n)."""
+    if world <= 0 or not (0 <= rank < world) or block <= 0:
+        raise ValueError("rank/world/block out of range")
+    return [(lo, min(lo + block, n)) for lo in range(rank * block, n, world * block)]
+
+
+def take_shard(points: np.ndarray, ranges) -> np.ndarray:
+    """The rank's shard as one C-contiguous (k, 3) array: its ranges concatenated in order."""
+    if not ranges:
+        return np.empty((0, 3), dtype=np.float64)
+    return np.ascontiguousarray(np.concatenate([points[lo:hi] for lo, hi in ranges]))
+
+
+def put_shard(points: np.ndarray, ranges, shard: np.ndarray) -> None:
+    """Write a (moved) shard back into the caller's array, range by range (inverse of take_shard)."""
+    at = 0
+    for lo, hi in ranges:
+        points[lo:hi] = shard[at:at + (hi - lo)]
+        at += hi - lo
+
+
+def _spread10(v: np.ndarray) -> np.ndarray:
+    """10-bit integers -> bits at positions 0, 3, 6, ... (one axis of a 30-bit Morton key)."""
+    v = v.astype(np.uint32) & np.uint32(0x3FF)
+    v = (v | (v << np.uint32(16))) & np.uint32(0x030000FF)
+    v = (v | (v << np.uint32(8))) & np.uint32(0x0300F00F)
+    v = (v | (v << np.uint32(4))) & np.uint32(0x030C30C3)
+    v = (v | (v << np.uint32(2))) & np.uint32(0x09249249)
+    return v
+
+
+def spatial_order(points: np.ndarray) -> np.ndarray:
+    """Stable argsort of the points by a 30-bit Morton key over their own bounding cube (host side, once per cloud)."""
+    pts = np.asarray(points, dtype=np.float64)
+    if len(pts) == 0:
+        return np.empty(0, dtype=np.int64)
+    lo = pts.min(axis=0)
+    cube = float((pts.max(axis=0) - lo).max())
+    scale = 1023.999 / cube if cube > 0.0 else 0.0
+    q = np.clip((pts - lo) * scale, 0, 1023).astype(np.uint32)
+    key = _spread10(q[:, 0]) | (_spread10(q[:, 1]) << np.uint32(1)) | (_spread10(q[:, 2]) << np.uint32(2))
+    return np.argsort(key, kind="stable")
+
+
+def shard_spatial(points: np.ndarray, rank: int, world: int, order: np.ndarray | None = None) -> np.ndarray:
+    """Indices (ascending) of rank's shard when the cloud is first put in spatial (Morton) order and THEN cut into `world`
+    contiguous point ranges: every rank owns a compact region with the same number of points, so its queries touch only
+    that region's part of the replicated target structure (on 8 GPUs the NN stage of a randomly ordered 10 M-point cloud
+    runs twice as fast per query as with ranges of the caller's order).  A cloud that is already stored in scan order
+    gets the same effect from shard_range."""
+    order = spatial_order(points) if order is None else order
+    lo, hi = shard_range(len(order), rank, world)
+    return np.sort(order[lo:hi])
+
+
 def exchange_unique_id(handle, dist, rank: int, src: int = 0) -> bytes:
     """Rank `src` creates the NCCL unique id through the C ABI (icp_comm_unique_id); everyone receives it."""
     box = [handle.comm_unique_id() if rank == src else None]

@@ -28,6 +28,43 @@ def test_shard_ranges_tile_the_source():
         sharding.shard_range(10, 2, 2)
 
 
+def test_block_cyclic_ranges_tile_the_source_and_round_trip():
+    r = np.random.default_rng(4)
+    for n in (0, 1, 7, 1000, 300_017):
+        for world in (1, 2, 3, 8):
+            for block in (1, 64, 65536):
+                per_rank = [sharding.shard_blocks(n, k, world, block) for k in range(world)]
+                flat = sorted(x for rr in per_rank for x in rr)
+                assert (flat[0][0] == 0 and flat[-1][1] == n) if n else not flat
+                assert all(a[1] == b[0] for a, b in zip(flat, flat[1:]))
+                sizes = [sum(hi - lo for lo, hi in rr) for rr in per_rank]
+                assert max(sizes) - min(sizes) <= block
+    pts = r.normal(size=(1000, 3))
+    out = np.zeros_like(pts)
+    for k in range(3):
+        rr = sharding.shard_blocks(len(pts), k, 3, 64)
+        sh = sharding.take_shard(pts, rr)
+        assert sh.flags["C_CONTIGUOUS"] and len(sh) == sum(hi - lo for lo, hi in rr)
+        sharding.put_shard(out, rr, sh)
+    assert np.array_equal(out, pts)
+    with pytest.raises(ValueError):
+        sharding.shard_blocks(10, 0, 2, 0)
+
+
+def test_spatial_shards_partition_the_cloud_into_compact_equal_parts():
+    pts = synth.make_target(40_000, 5)
+    order = sharding.spatial_order(pts)
+    assert sorted(order.tolist()) == list(range(len(pts)))
+    world = 8
+    parts = [sharding.shard_spatial(pts, k, world, order) for k in range(world)]
+    assert sorted(np.concatenate(parts).tolist()) == list(range(len(pts)))
+    assert max(map(len, parts)) - min(map(len, parts)) <= 1
+    # compact: a shard's bounding box covers far less than the cloud's (a range of the random caller order covers all of it)
+    area = lambda p: float(np.prod((p.max(0) - p.min(0))[:2]))
+    assert max(area(pts[i]) for i in parts) < 0.5 * area(pts) and np.mean([area(pts[i]) for i in parts]) < 0.3 * area(pts)
+    assert len(sharding.spatial_order(np.empty((0, 3)))) == 0
+
+
 def test_rank_ordered_merge_matches_whole_cloud_statistics():
     r = np.random.default_rng(0)
     d = np.abs(r.normal(size=100_003)) * 0.3
