@@ -388,9 +388,10 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         const IterRecord rec = *c->h_rec;
         if (c->opt_count && getenv("ICP_B200_DEBUG_ITER")) {  // profiling aid: counters and work-list lengths of this iteration
             unsigned long long w[8];
-            unsigned int wc[2];
+            unsigned int wc[16];
             cudaMemcpy(w, c->d_counters, sizeof w, cudaMemcpyDeviceToHost);
             cudaMemcpy(wc, c->d_work_count, sizeof wc, cudaMemcpyDeviceToHost);
+            for (int k = 2; k < 10; ++k) wc[0] += wc[k];  // the balanced walk keeps one list per chunk of queries
             fprintf(stderr, "[icp_b200] iter %d nn %.3f ms: settled=%llu literal=%llu slow=%llu candidates=%llu items=%llu kept=%llu | list1=%u list2=%u\n",
                     iter, nn_ms, w[0], w[1], w[2], w[3], w[4], w[5], wc[0], wc[1]);
             cudaMemset(c->d_counters, 0, sizeof w);
@@ -550,12 +551,19 @@ int icp_create(icp_handle* out, int device_id) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaEventCreateWithFlags(&c->ev_src, cudaEventDisableTiming) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    {
+        int lo_prio = 0, hi_prio = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+        if (cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, hi_prio) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+        for (auto& e : c->ev_chunk)
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    }
     for (auto& e : c->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaMalloc(&c->d_state, sizeof(LoopState)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long));
-    if (cudaMalloc(&c->d_work_count, 2 * sizeof(unsigned int)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    if (cudaMalloc(&c->d_work_count, 16 * sizeof(unsigned int)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaHostAlloc(&c->h_rec, sizeof(IterRecord), cudaHostAllocMapped) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaHostGetDevicePointer(&c->d_rec, c->h_rec, 0) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (getenv("ICP_B200_DEBUG_COUNTERS")) c->opt_count = true;
@@ -587,6 +595,9 @@ void icp_destroy(icp_handle h) {
         if (e) cudaEventDestroy(e);
     if (c->ev_src) cudaEventDestroy(c->ev_src);
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->stream_hi) cudaStreamDestroy(c->stream_hi);
+    for (auto& e : c->ev_chunk)
+        if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c->nccl;
     delete c;
@@ -651,6 +662,7 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     else if (!strcmp(key, "terminal_pts")) c->opt_terminal_pts = std::min(std::max((int)value, 1), 1024);
     else if (!strcmp(key, "search_leaf")) c->opt_search_leaf = std::min(std::max((int)value, 1), 1024);
     else if (!strcmp(key, "order_queries")) c->opt_order_queries = value != 0.0;
+    else if (!strcmp(key, "nn_chunks")) c->opt_nn_chunks = std::min(std::max((int)value, 1), 8);
     else if (!strcmp(key, "temporal_skip")) c->opt_temporal_skip = value != 0.0;
     else if (!strcmp(key, "keep_k")) { c->opt_keep_k = std::min(std::max((int)value, 1), 4); c->keep_valid = false; }
     else if (!strcmp(key, "keep_alpha")) c->opt_keep_alpha = std::min(std::max(value, 1.0), 16.0);

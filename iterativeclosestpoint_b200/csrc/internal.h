@@ -47,6 +47,10 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // source upload, overlapped with the target's tree build
+    cudaStream_t stream_hi = nullptr;  // higher priority: the work-list kernel of one chunk of queries runs beside the next chunk's walk
+    cudaEvent_t ev_chunk[9] = {};
+    int opt_nn_chunks = 1;           // modes 4 / 6: walk the queries in this many chunks (>= 2^20 queries), work lists overlapped; measured
+                                     // neutral on the 10^7-point scenes (helps once the registration has nearly converged, costs before)
     cudaEvent_t ev_src = nullptr;
     cudaEvent_t ev[12] = {};
     DevBuf pin_a, pin_b;       // pinned host staging (grow-only), batch path

@@ -227,20 +227,48 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
         // the balanced kernel settles what it can; the per-thread kernel (cell walk, then climb / literal) takes the rest
         const bool in_place = !L.apply_pending || (L.ox == L.sx && L.oy == L.sy && L.oz == L.sz);
         if (in_place && c->d_work_count && c->node_io.p) {
-            A.worklist = (uint32_t*)c->node_io.p;
-            A.work_count = c->d_work_count;
-            A.gkmin = 0;
-            ICPB_CUDA(c, cudaMemsetAsync(c->d_work_count, 0, sizeof(unsigned int), c->stream));
-            ICPB_TRY(A.lb_io ? nn_group_launch(c, A) : nn_group_lean_launch(c, A));
-            A.gkmin = A.gbase;
-            A.mode = 3;
-            if (c->opt_walk_bias == -100) A.gbias = -2;
-            A.gbias_mul = std::ldexp(1.0, -A.gbias);
-            A.apply_pending = 0;
-            A.node_io = nullptr;
-            nn_kernel<<<nn_grid_blocks(L.n), NN_THREADS, 0, c->stream>>>(A);
-            c->launches++;
-            ICPB_CUDA(c, cudaGetLastError());
+            // Optionally (nn_chunks > 1) the queries are walked in chunks: while the balanced kernel walks chunk k + 1, the
+            // per-thread kernel works off chunk k's list on a higher-priority stream, so that its few, long searches fill
+            // issue slots the walk leaves idle instead of standing alone at the end of the stage.
+            const int nchunk = (L.n >= (1 << 20) && !A.counters) ? std::min(std::max(c->opt_nn_chunks, 1), 8) : 1;
+            ICPB_CUDA(c, cudaMemsetAsync(c->d_work_count, 0, 16 * sizeof(unsigned int), c->stream));
+            const int walk_bias = A.gbias;
+            for (int k = 0; k < nchunk; ++k) {
+                const long long lo = ((L.n * k / nchunk) + 127) / 128 * 128, hi = (k + 1 == nchunk) ? L.n : ((L.n * (k + 1) / nchunk) + 127) / 128 * 128;
+                if (hi <= lo) continue;
+                NNArgs B = A;
+                B.sx += lo; B.sy += lo; B.sz += lo;
+                if (B.ox) { B.ox += lo; B.oy += lo; B.oz += lo; }
+                B.pos_out += lo; B.dist_out += lo;
+                if (B.prev_pos) B.prev_pos += lo;
+                if (B.lb_io) B.lb_io += lo;
+                B.n = hi - lo;
+                B.worklist = (uint32_t*)c->node_io.p + lo;  // entries are indices relative to the chunk
+                B.work_count = c->d_work_count + 2 + k;
+                B.gkmin = 0;
+                B.gbias = walk_bias;
+                B.gbias_mul = std::ldexp(1.0, -B.gbias);
+                ICPB_TRY(B.lb_io ? nn_group_launch(c, B) : nn_group_lean_launch(c, B));
+                cudaStream_t fs = c->stream;
+                if (nchunk > 1) {
+                    ICPB_CUDA(c, cudaEventRecord(c->ev_chunk[k], c->stream));
+                    ICPB_CUDA(c, cudaStreamWaitEvent(c->stream_hi, c->ev_chunk[k], 0));
+                    fs = c->stream_hi;
+                }
+                B.gkmin = B.gbase;
+                B.mode = 3;
+                B.gbias = c->opt_walk_bias != -100 ? c->opt_walk_bias : -2;
+                B.gbias_mul = std::ldexp(1.0, -B.gbias);
+                B.apply_pending = 0;
+                B.node_io = nullptr;
+                nn_kernel<<<nn_grid_blocks(B.n), NN_THREADS, 0, fs>>>(B);
+                c->launches++;
+                ICPB_CUDA(c, cudaGetLastError());
+            }
+            if (nchunk > 1) {
+                ICPB_CUDA(c, cudaEventRecord(c->ev_chunk[8], c->stream_hi));
+                ICPB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_chunk[8], 0));
+            }
             return ICP_OK;
         }
         A.mode = 3;

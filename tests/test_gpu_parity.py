@@ -447,6 +447,22 @@ def test_full_size_config3_sample_parity_and_properties(handle, oracle):
     assert np.array_equal(idx2[sample], otree.find_nearest(moved[sample], nthreads=oracle.hw_threads()))
     # inlier counts of the three iterations against the oracle's statistics on the GPU's own correspondences
     assert all(h.validPoints + h.outlierPoints == len(src) for h in res.iterationHistory)
+    # the whole registration to convergence at full size: the default mode (balanced walk, then keep / collect with bounds
+    # carried between iterations) must reproduce the one-thread-per-query walk bit for bit -- every index and distance of
+    # every iteration feeds the order-deterministic sums behind these numbers
+    runs = {}
+    for mode in (3, 6):
+        handle.set_option("nn_mode", mode)
+        handle.set_params(ICPParameters(maxIterations=20, tolerance=1e-15))
+        work = src.copy()
+        runs[mode] = handle.register(work, tgt)
+        del work
+    a, b = runs[3], runs[6]
+    assert a.loopIterations == b.loopIterations == 20
+    assert np.array_equal(a.cumulativeT, b.cumulativeT)
+    assert [h.rmse for h in a.iterationHistory] == [h.rmse for h in b.iterationHistory]
+    assert [h.validPoints for h in a.iterationHistory] == [h.validPoints for h in b.iterationHistory]
+    assert b.iterationHistory[-1].nnMs < 0.5 * b.iterationHistory[3].nnMs  # the converged iterations take the keep path
 
 
 def test_balanced_walk_with_temporal_skip_is_bit_identical_to_the_per_thread_walk(handle):
