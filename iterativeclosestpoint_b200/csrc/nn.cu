@@ -106,11 +106,20 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
     if (A.worklist) {
         // second half of mode 4: the queries nn_group_kernel could not settle (already moved, matches untouched).
         // One query per thread while the list is shorter than the grid; the surplus blocks exit at once.
+        // These are the hard queries and every one is a chain of dependent loads, so a short list is spread thin: only the
+        // first `act` lanes of a warp take entries while that still leaves the list within the warps the GPU holds at once
+        // (a quarter as many queries per warp = a quarter of the divergent work in front of its slowest lane).
         const long long cnt = (long long)*A.work_count;
-        for (long long t = i; t < cnt; t += (long long)gridDim.x * NN_THREADS) {
-            fell_back = false;
-            nn_one_query(A, (long long)A.worklist[t], true, stk, st, fell_back);
-            if (A.counters) atomicAdd(&A.counters[fell_back ? 1 : 0], 1ull);
+        const int lane = threadIdx.x & 31;
+        const long long n_warps = ((long long)gridDim.x * NN_THREADS) >> 5;
+        int act = 32;
+        while (act > 4 && cnt * (64 / act) <= A.resident_threads && cnt * 2 <= n_warps * act) act >>= 1;
+        if (lane < act) {
+            for (long long t = (i >> 5) * act + lane; t < cnt; t += n_warps * act) {
+                fell_back = false;
+                nn_one_query(A, (long long)A.worklist[t], true, stk, st, fell_back);
+                if (A.counters) atomicAdd(&A.counters[fell_back ? 1 : 0], 1ull);
+            }
         }
         return;
     }
@@ -157,6 +166,7 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
     A.grid = c->fast.grid;
     A.glmin = c->fast.glev_min;
     A.gnlev = c->fast.glev_n;
+    A.resident_threads = (long long)c->sm_count * 7 * NN_THREADS;  // nn_kernel: 7 blocks per SM (registers)
     A.gbase = c->fast.gbase;
     A.gkmin = c->fast.gbase;  // the per-thread walks stay on the base level and finer; the balanced kernels may go coarser
     A.gmax_cells = c->opt_walk_max_cells;

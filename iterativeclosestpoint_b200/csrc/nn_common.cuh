@@ -54,6 +54,7 @@ struct NNArgs {
     uint32_t* worklist2;       // mode 5: queries handed on to the per-thread kernel (count at work_count[1])
     double walk_alpha, walk_wmul, walk_rcap;  // mode 5: search ball = seed radius x alpha, widened up to rcap at most; level = finest
                                // with cell edge >= ball radius x wmul
+    long long resident_threads; // threads of nn_kernel the GPU holds at once (work-list spreading)
     uint32_t* worklist;        // mode 4: queries the balanced kernel hands to the per-thread kernel ...
     unsigned int* work_count;  // ... and how many; the per-thread kernel runs over that list when worklist != null
     double init_best;
