@@ -128,10 +128,18 @@ int icp_get_params(icp_handle h, icp_params* p);                /* ICPEngine::ge
 void icp_default_params(icp_params* p);                         /* ICPParameters defaults (icpengine.h:13-19) */
 int icp_set_callbacks(icp_handle h, icp_iteration_cb on_iteration, icp_progress_cb on_progress, icp_log_cb on_log,
                       void* user);
-/* Tuning knobs that never change results: "nn_mode" (0 = literal reference traversal from the root, one query per
- * thread; 1 = per-thread order-independent search with literal fallback; 2 = warp tiles with shared-memory staged
- * candidates, per-thread and literal fallbacks -- the default), "order_queries" (Morton-order the source internally,
- * default 1), "write_mask" (keep the inlier mask). */
+/* Tuning knobs that never change results (every search mode returns the reference's indices):
+ *   "nn_mode"  0 literal reference traversal from the root, one query per thread; 1 per-thread climbing search;
+ *              2 warp tiles with shared-memory staged candidates; 3 per-thread walk over the entry-grid cells the search
+ *              ball touches; 4 the same walk with the candidate scan balanced over the warp; 5 keep / collect: candidates
+ *              and a lower bound carried between iterations settle a query without a search; 6 (default) mode 4 while
+ *              the registration moves, mode 5 once it has nearly converged -- all with the literal traversal as fallback;
+ *   "keep_k" "keep_alpha" "keep_rcap" "keep_bias" "keep_enter" "keep_exit"   the keep / collect path (modes 5, 6);
+ *   "grid_levels" "grid_coarse" "grid_max_cells" "grid_shift" "base_occupancy" "range_max"   the entry-grid pyramid;
+ *   "search_leaf" "search_depth" "terminal_pts" "walk_bias" "walk_max_cells" "nn_chunks" "temporal_skip"   search details;
+ *   "order_queries" (Morton-order the source internally, default 1), "write_mask" (keep the inlier mask),
+ *   "batch_small" "batch_workers" (icp_register_batch: one-block kernel for small pairs, worker streams), "count" (profiling
+ *   counters). */
 int icp_set_option(icp_handle h, const char* key, double value);
 
 /* ---- the whole hot path, HOST buffers in and out ------------------------------------------------- */
