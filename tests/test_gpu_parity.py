@@ -544,3 +544,42 @@ def test_keep_and_search_on_tie_heavy_clouds_matches_the_literal_traversal(handl
         assert [h.validPoints for h in b.iterationHistory] == [h.validPoints for h in a.iterationHistory]
         assert [h.rmse for h in b.iterationHistory] == [h.rmse for h in a.iterationHistory]
         assert np.array_equal(runs[0][1], runs[mode][1])
+
+
+@pytest.mark.parametrize("shape", ["volume", "clusters", "plane", "line", "tiny"])
+def test_search_modes_agree_on_clouds_that_are_not_terrain(handle, shape):
+    """The entry-grid pyramid, the point-spacing estimate behind the mode-6 hand-over and the keep / collect radii are tuned
+    on 2.5-D scenes; results must not depend on that.  Volumetric, clustered, planar, collinear and tiny clouds: whole runs
+    in every search mode equal the literal traversal (nn_mode 0) bit for bit."""
+    rng = np.random.default_rng({"volume": 1, "clusters": 2, "plane": 3, "line": 4, "tiny": 5}[shape])
+    if shape == "volume":
+        tgt = rng.uniform(0.0, 20.0, size=(150_000, 3))
+    elif shape == "clusters":
+        centres = rng.uniform(-50.0, 50.0, size=(40, 3))
+        tgt = np.concatenate([c + rng.normal(scale=s, size=(3000, 3)) for c, s in zip(centres, rng.uniform(0.05, 3.0, 40))])
+    elif shape == "plane":
+        xy = rng.uniform(0.0, 60.0, size=(120_000, 2))
+        tgt = np.column_stack([xy, 0.3 * xy[:, 0] - 0.1 * xy[:, 1] + 5.0])
+    elif shape == "line":
+        t = rng.uniform(0.0, 100.0, size=20_000)
+        tgt = np.column_stack([t, 2.0 * t + 1.0, -0.5 * t])
+    else:
+        tgt = rng.uniform(0.0, 1.0, size=(7, 3))
+    tgt = np.ascontiguousarray(tgt)
+    R = synth.rotation_zyx(0.004, -0.002, 0.003)
+    c0 = tgt.mean(0)
+    src = np.ascontiguousarray((tgt - c0) @ R.T + c0 + np.array([0.02, -0.015, 0.01]) + rng.normal(scale=0.002, size=tgt.shape))
+    runs = {}
+    for mode in (0, 3, 4, 5, 6):
+        handle.set_option("nn_mode", mode)
+        handle.set_params(ICPParameters(maxIterations=10, tolerance=1e-15))
+        work = src.copy()
+        runs[mode] = (handle.register(work, tgt), work)
+    a = runs[0][0]
+    for mode in (3, 4, 5, 6):
+        b = runs[mode][0]
+        assert b.loopIterations == a.loopIterations and b.success == a.success, (shape, mode)
+        assert np.array_equal(b.cumulativeT, a.cumulativeT), (shape, mode)
+        assert [h.validPoints for h in b.iterationHistory] == [h.validPoints for h in a.iterationHistory], (shape, mode)
+        assert [h.rmse for h in b.iterationHistory] == [h.rmse for h in a.iterationHistory], (shape, mode)
+        assert np.array_equal(runs[mode][1], runs[0][1]), (shape, mode)
