@@ -115,6 +115,7 @@ struct Ctx {
     Mailbox* mail = nullptr;
     Mailbox* peer_mail[MAIL_RANKS] = {};
     bool p2p = false;
+    bool rs_smem_opt_in = false;  // radix_scatter_kernel's dynamic shared memory opt-in done for this handle's device
     unsigned int mail_epoch = 0;
     unsigned long long* d_counters = nullptr;  // see NNArgs::counters (4 entries)
     unsigned int* d_work_count = nullptr;      // mode 4/5: lengths of the two work lists (node_io, work2)
