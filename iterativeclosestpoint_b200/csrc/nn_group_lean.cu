@@ -29,6 +29,10 @@ struct __align__(16) GlSlot {
     double qx, qy, qz, bound;
 };
 
+// SEED: queries without a previous match look for a seed in their own base cell (first iteration, stateless queries).  Later
+// iterations run the instance without that code (a fifth of the kernel's instructions, never executed there: less pressure on
+// the instruction cache); a query that has no match then simply goes on the work list.
+template <bool SEED>
 __global__ void __launch_bounds__(GW_THREADS) nn_group_lean_kernel(const NNArgs A) {
     __shared__ GlSlot slot_all[GW_WARPS][32];
     __shared__ uint2 queue_all[GW_WARPS][GW_QCAP];   // item: x = first point, y = count | owner lane << 8; result: x = position, y = tie
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(GW_THREADS) nn_group_lean_kernel(const NNArgs 
                 load_point(A.pts, pp, px, py, pz, pidx);
                 Sd = sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz));
             }
-            if (!(Sd < 1e19)) Sd = walk_seed(A, qx, qy, qz);
+            if (SEED && !(Sd < 1e19)) Sd = walk_seed(A, qx, qy, qz);
         }
         if (Sd < 1e19) {
             // the same ball, level and cell range as cell_walk (nn_common.cuh)
@@ -239,7 +243,10 @@ __global__ void __launch_bounds__(GW_THREADS) nn_group_lean_kernel(const NNArgs 
 
 int nn_group_lean_launch(Ctx* c, const NNArgs& A) {
     const int blocks = (int)((A.n + GW_THREADS - 1) / GW_THREADS);
-    nn_group_lean_kernel<<<blocks, GW_THREADS, 0, c->stream>>>(A);
+    if (A.prev_pos)
+        nn_group_lean_kernel<false><<<blocks, GW_THREADS, 0, c->stream>>>(A);
+    else
+        nn_group_lean_kernel<true><<<blocks, GW_THREADS, 0, c->stream>>>(A);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
     return ICP_OK;
