@@ -2,6 +2,7 @@
 // (replaces ICPEngine::registerPointClouds / runICP, core/icpengine.cpp:24-60,117-394, and the CLI's ICP(),
 // icp_registration.cpp:443-622) and the sharded multi-GPU driver.
 #include "internal.h"
+#include "nn_common.cuh"
 #include <nccl.h>
 #include <dlfcn.h>
 #include <cmath>
@@ -29,7 +30,7 @@ int pairs_b_launch(Ctx* c, const double* a_xyz, const double* b_xyz, int64_t n, 
 int solve_launch(Ctx* c, const double* rank_parts, int n_ranks);
 int bestfit_launch(Ctx* c, const double* b17, const double* a0, const double* b0, double* T_out);
 int solve_from_H_launch(Ctx* c, const double* in15, double* out37);
-int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n, float* lb = nullptr);
+int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n, float* lb = nullptr, float* eb = nullptr);
 int unsort_results_launch(Ctx* c, const uint32_t* pos, const double* dist, const uint32_t* perm, int64_t n, int32_t* idx_out,
                           double* dist_out);
 int aos_to_soa_launch(Ctx* c, const double* xyz, int64_t n, double* sx, double* sy, double* sz);
@@ -106,9 +107,12 @@ static int ensure_run_buffers(Ctx* c, int64_t n) {
     ICPB_TRY(devbuf_reserve(c, c->mask, (size_t)n));
     ICPB_TRY(devbuf_reserve(c, c->node_io, (size_t)n * sizeof(uint32_t)));
     ICPB_TRY(devbuf_reserve(c, c->lb, (size_t)n * sizeof(float)));
-    if (c->opt_nn_mode >= 5) {
-        ICPB_TRY(devbuf_reserve(c, c->cand, (size_t)n * sizeof(uint4)));
-        ICPB_TRY(devbuf_reserve(c, c->work2, (size_t)n * sizeof(uint32_t)));
+    if (c->opt_nn_mode == 5 || c->opt_nn_mode == 6) ICPB_TRY(devbuf_reserve(c, c->cand, (size_t)n * sizeof(uint4)));
+    if (c->opt_nn_mode >= 5) ICPB_TRY(devbuf_reserve(c, c->work2, (size_t)n * sizeof(uint32_t)));
+    if (c->opt_nn_mode == 7 && c->groups_n == n && c->n_groups > 0) {  // carried candidate lists of the query groups (nn_box.cu)
+        ICPB_TRY(devbuf_reserve(c, c->lhdr, (size_t)c->n_groups * sizeof(BoxListHdr)));
+        ICPB_TRY(devbuf_reserve(c, c->lcand, (size_t)c->n_groups * BOX_LIST_CAP * sizeof(float4)));
+        ICPB_TRY(devbuf_reserve(c, c->lpos, (size_t)c->n_groups * BOX_LIST_CAP * sizeof(uint32_t)));
     }
     const size_t nbA = (size_t)std::max<int64_t>(stat_a_blocks(c, n), (n + 255) / 256 / 4) + 1024;
     ICPB_TRY(devbuf_reserve(c, c->part_a, nbA * sizeof(StatA)));
@@ -157,6 +161,7 @@ static int source_from_device_aos(Ctx* c, const double* d_xyz, int64_t n) {
     if (c->opt_order_queries && n > 1)
         return order_queries(c, d_xyz, n, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p, (uint32_t*)c->sperm.p);
     c->src_identity_perm = true;
+    ICPB_TRY(make_fixed_groups(c, n));
     return aos_to_soa_launch(c, d_xyz, n, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p);
 }
 
@@ -289,6 +294,7 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
 
     const bool resume = c->prev_valid;  // same resident source and tree as the last run: its matches seed this one
     c->prev_valid = false;
+    if (!resume || c->opt_nn_mode != 7) c->lists_valid = false;
     if (c->opt_nn_mode == 2 && !resume)  // per-tile start nodes: the root until a tile has searched once
         ICPB_CUDA(c, cudaMemsetAsync(c->node_io.p, 0, (size_t)((n + 31) / 32) * sizeof(uint32_t), c->stream));
     if (c->opt_nn_mode == 4)  // temporal bounds belong to one run: the source moves between runs
@@ -405,7 +411,9 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     *write_back = acc.write_back;
     if (acc.write_back)  // the last T, if any
         ICPB_TRY(apply_pending_launch(c, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p, n,
-                                      (c->opt_nn_mode == 5 || phase >= 1) ? (float*)c->lb.p : nullptr));
+                                      (c->opt_nn_mode == 5 || phase >= 1) ? (float*)c->lb.p : nullptr,
+                                      (c->opt_nn_mode == 7 && c->lists_valid) ? (float*)c->lb.p : nullptr));
+    if (!c->prev_valid) c->lists_valid = false;
     c->keep_valid = c->prev_valid && acc.write_back && (c->opt_nn_mode == 5 || phase >= 1) && c->opt_temporal_skip;
     c->last_rmse = prev_rmse;
     acc.finish();
@@ -568,7 +576,7 @@ int icp_create(icp_handle* out, int device_id) {
     if (cudaHostGetDevicePointer(&c->d_rec, c->h_rec, 0) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (getenv("ICP_B200_DEBUG_COUNTERS")) c->opt_count = true;
     const char* m = getenv("ICP_B200_NN_MODE");
-    if (m) c->opt_nn_mode = std::min(std::max(atoi(m), 0), 6);
+    if (m) c->opt_nn_mode = std::min(std::max(atoi(m), 0), 7);
     *out = (icp_handle)c;
     return ICP_OK;
 }
@@ -583,7 +591,7 @@ void icp_destroy(icp_handle h) {
     c->workers.clear();
     octree_free(c);
     DevBuf* bufs[] = {&c->tgt_raw, &c->sx, &c->sy, &c->sz, &c->sperm, &c->pos, &c->dist, &c->mask, &c->part_a, &c->part_b,
-                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt, &c->lb, &c->cand, &c->work2};
+                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt, &c->lb, &c->cand, &c->work2, &c->gstart, &c->lhdr, &c->lcand, &c->lpos};
     for (DevBuf* b : bufs) devbuf_free(*b);
     if (c->pin_a.p) cudaFreeHost(c->pin_a.p);
     if (c->pin_b.p) cudaFreeHost(c->pin_b.p);
@@ -644,7 +652,7 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     Ctx* c = (Ctx*)h;
     if (!c || !key) return ICP_INVALID_ARGUMENT;
     if (!strcmp(key, "nn_mode")) {
-        c->opt_nn_mode = value < 0.5 ? 0 : (value < 1.5 ? 1 : (value < 2.5 ? 2 : (value < 3.5 ? 3 : (value < 4.5 ? 4 : (value < 5.5 ? 5 : 6)))));
+        c->opt_nn_mode = std::min(std::max((int)(value + 0.5), 0), 7);
         c->prev_valid = false;
     }
     else if (!strcmp(key, "count")) c->opt_count = value != 0.0;
@@ -671,6 +679,11 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     else if (!strcmp(key, "keep_rcap")) c->opt_keep_rcap = std::min(std::max(value, 0.0), 8.0);
     else if (!strcmp(key, "keep_bias")) c->opt_keep_bias = std::min(std::max((int)value, -4), 4);
     else if (!strcmp(key, "write_mask")) c->opt_write_mask = value != 0.0;
+    else if (!strcmp(key, "box_guess")) c->opt_box_guess = std::min(std::max(value, 0.01), 4.0);
+    else if (!strcmp(key, "box_emax")) c->opt_box_emax = std::min(std::max(value, 0.01), 8.0);
+    else if (!strcmp(key, "box_skin")) { c->opt_box_skin = std::min(std::max(value, 0.0), 2.0); c->lists_valid = false; }
+    else if (!strcmp(key, "box_lists")) { c->opt_box_lists = value != 0.0; c->lists_valid = false; }
+    else if (!strcmp(key, "box_tighten")) c->opt_box_tighten = std::min(std::max(value, -1.0), 8.0);
     else {
         c->err = std::string("unknown option ") + key;
         return ICP_INVALID_ARGUMENT;
@@ -893,6 +906,7 @@ int icp_iteration_stats(icp_handle h, const double* src_xyz, int64_t n, const in
     ICPB_CUDA(c, cudaSetDevice(c->device));
     ICPB_TRY(build_inv_perm(c));
     c->prev_valid = false;
+    c->lists_valid = false;
     ICPB_TRY(upload(c, c->scratch_src, src_xyz, n));
     ICPB_TRY(ensure_source_buffers(c, n));
     ICPB_TRY(ensure_run_buffers(c, n));

@@ -491,7 +491,7 @@ __device__ __forceinline__ void apply_T(const double* T, double& x, double& y, d
 // applies state->T_pending if state->have_T (used once at loop exit)
 __global__ void __launch_bounds__(256) apply_pending_kernel(const LoopState* __restrict__ st, double* __restrict__ x,
                                                             double* __restrict__ y, double* __restrict__ z, int64_t n,
-                                                            float* __restrict__ lb) {
+                                                            float* __restrict__ lb, float* __restrict__ eb) {
     if (!st->have_T) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -504,6 +504,10 @@ __global__ void __launch_bounds__(256) apply_pending_kernel(const LoopState* __r
     if (lb) {  // nn_keep.cu: the bound holds for where the point was; it moved by at most this much
         const double moved = dmul(dsqrt(sumsq3(dsub(a, oa), dsub(b, ob), dsub(c, oc))), 1.0 + 1e-9);
         lb[i] = __double2float_rd(dsub((double)lb[i], moved));
+    }
+    if (eb) {  // nn_box.cu: the match is at most this much farther away from where the point is now
+        const double moved = dmul(dsqrt(sumsq3(dsub(a, oa), dsub(b, ob), dsub(c, oc))), 1.0 + 1e-9);
+        eb[i] = __double2float_ru(dadd((double)eb[i], moved));
     }
 }
 
@@ -554,8 +558,8 @@ __global__ void __launch_bounds__(256) aos_to_soa_kernel(const double* __restric
 
 static inline int nblk(int64_t n) { return (int)((n + 255) / 256); }
 
-int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n, float* lb) {
-    apply_pending_kernel<<<nblk(n), 256, 0, c->stream>>>(c->d_state, x, y, z, n, lb);
+int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n, float* lb, float* eb) {
+    if (n > 0) apply_pending_kernel<<<nblk(n), 256, 0, c->stream>>>(c->d_state, x, y, z, n, lb, eb);
     clear_pending_kernel<<<1, 32, 0, c->stream>>>(c->d_state);
     c->launches += 2;
     ICPB_CUDA(c, cudaGetLastError());
@@ -563,6 +567,7 @@ int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n, flo
 }
 
 int apply_aos_launch(Ctx* c, const double* d_T16, double* xyz, int64_t n) {
+    if (n <= 0) return ICP_OK;
     apply_aos_kernel<<<nblk(n), 256, 0, c->stream>>>(d_T16, xyz, n);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
@@ -571,6 +576,7 @@ int apply_aos_launch(Ctx* c, const double* d_T16, double* xyz, int64_t n) {
 
 int unsort_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const uint32_t* perm, int64_t n,
                   double* out_xyz) {
+    if (n <= 0) return ICP_OK;
     unsort_kernel<<<nblk(n), 256, 0, c->stream>>>(sx, sy, sz, perm, n, out_xyz);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
@@ -579,6 +585,7 @@ int unsort_launch(Ctx* c, const double* sx, const double* sy, const double* sz, 
 
 int unsort_results_launch(Ctx* c, const uint32_t* pos, const double* dist, const uint32_t* perm, int64_t n, int32_t* idx_out,
                           double* dist_out) {
+    if (n <= 0) return ICP_OK;
     unsort_results_kernel<<<nblk(n), 256, 0, c->stream>>>(pos, dist, perm, c->fast.pts, n, idx_out, dist_out);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
@@ -586,6 +593,7 @@ int unsort_results_launch(Ctx* c, const uint32_t* pos, const double* dist, const
 }
 
 int aos_to_soa_launch(Ctx* c, const double* xyz, int64_t n, double* sx, double* sy, double* sz) {
+    if (n <= 0) return ICP_OK;
     aos_to_soa_kernel<<<nblk(n), 256, 0, c->stream>>>(xyz, n, sx, sy, sz);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
