@@ -25,9 +25,10 @@ int dist_from_idx_launch(Ctx* c, const double* sx, const double* sy, const doubl
                          uint32_t* pos_out, double* dist_out, StatA* part, int* n_part);
 int stage_b_blocks(Ctx* c, int64_t n);
 int stage_b_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const uint32_t* pos, const double* dist,
-                   int64_t n, int iter, const StatA* rank_a, uint8_t* mask_out, double* part, double* rank_b, const PeerMail* pm = nullptr);
+                   int64_t n, int iter, const StatA* rank_a, uint8_t* mask_out, double* part, double* rank_b, const PeerMail* pm = nullptr,
+                   IterRecord* rec = nullptr);
 int pairs_b_launch(Ctx* c, const double* a_xyz, const double* b_xyz, int64_t n, double* part, double* out17);
-int solve_launch(Ctx* c, const double* rank_parts, int n_ranks);
+int solve_launch(Ctx* c, const double* rank_parts, int n_ranks, IterRecord* rec = nullptr);
 int bestfit_launch(Ctx* c, const double* b17, const double* a0, const double* b0, double* T_out);
 int solve_from_H_launch(Ctx* c, const double* in15, double* out37);
 int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n, float* lb = nullptr, float* eb = nullptr);
@@ -113,6 +114,12 @@ static int ensure_run_buffers(Ctx* c, int64_t n) {
         ICPB_TRY(devbuf_reserve(c, c->lhdr, (size_t)c->n_groups * sizeof(BoxListHdr)));
         ICPB_TRY(devbuf_reserve(c, c->lcand, (size_t)c->n_groups * BOX_LIST_CAP * sizeof(float4)));
         ICPB_TRY(devbuf_reserve(c, c->lpos, (size_t)c->n_groups * BOX_LIST_CAP * sizeof(uint32_t)));
+        const size_t had = c->gflag.cap;
+        ICPB_TRY(devbuf_reserve(c, c->gflag, (size_t)c->n_groups * sizeof(unsigned int)));
+        if (c->gflag.cap != had) {  // fresh storage: no group has asked for a rebuild in any epoch yet
+            ICPB_CUDA(c, cudaMemsetAsync(c->gflag.p, 0, c->gflag.cap, c->stream));
+            c->box_epoch = 0u;
+        }
     }
     const size_t nbA = (size_t)std::max<int64_t>(stat_a_blocks(c, n), (n + 255) / 256 / 4) + 1024;
     ICPB_TRY(devbuf_reserve(c, c->part_a, nbA * sizeof(StatA)));
@@ -279,6 +286,8 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     hs.variant = variant;
     hs.max_iterations = P.max_iterations;
     hs.n_global = n_global;
+    hs.rebuild_ratio = c->opt_box_rebuild;
+    hs.rmse_build = (c->prev_valid && c->lists_valid && c->opt_nn_mode == 7) ? c->rmse_build : 0.0;
     ICPB_CUDA(c, cudaMemcpyAsync(c->d_state, &hs, sizeof hs, cudaMemcpyHostToDevice, c->stream));
 
     RunAcc acc(c, out, variant, P.max_iterations, (long long)n_global);
@@ -313,15 +322,28 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     int phase = (c->opt_nn_mode == 6 && keep_state) ? 2 : 0;
     double prev_rmse = (c->opt_nn_mode == 6 && resume) ? c->last_rmse : -1.0;
     ICPB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-    for (int iter = 0; iter < P.max_iterations; ++iter) {
+    // The device decides when the loop ends (solve_step: LoopState::exit_code); every kernel of an iteration returns at once
+    // when it already has.  So the host may enqueue several iterations before it reads their records: no round trip per
+    // iteration.  A callback, a stop flag, the host-side mode schedule of nn_mode 6 or the per-iteration debug counters need
+    // every record as it is produced (the reference calls back and polls stop() once per iteration, icpengine.cpp:160-164,364-367).
+    const bool debug_iter = c->opt_count && getenv("ICP_B200_DEBUG_ITER");
+    const bool each = stop_flag || c->on_iteration || c->on_progress || c->on_log || debug_iter ||
+                      !(c->opt_nn_mode == 0 || c->opt_nn_mode == 1 || c->opt_nn_mode == 3 || c->opt_nn_mode == 7);
+    const int ahead = each ? 1 : std::min(std::max(c->opt_lookahead, 1), (int)Ctx::REC_RING);
+    bool go_on = true;
+    for (int iter0 = 0; iter0 < P.max_iterations && go_on; iter0 += ahead) {
+    const int n_batch = std::min(ahead, P.max_iterations - iter0);
+    for (int slot = 0; slot < n_batch; ++slot) {
+        const int iter = iter0 + slot;
         if (variant == ICP_VARIANT_ENGINE && stop_flag && *stop_flag) {  // icpengine.cpp:160-164
             log_msg(c, "registration stopped");
             out->status = ICP_CANCELLED;
             acc.write_back = false;
+            go_on = false;
             break;
         }
         log_msg(c, "iteration %d/%d ...", iter + 1, P.max_iterations);
-        out->loop_iterations = iter + 1;
+        c->h_rec[slot].iteration = 0;  // (an iteration that found the loop ended leaves its record untouched)
 
         NNLaunch L;
         L.sx = (double*)c->sx.p; L.sy = (double*)c->sy.p; L.sz = (double*)c->sz.p;
@@ -333,7 +355,7 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         L.node_io = (c->opt_nn_mode == 1) ? (uint32_t*)c->node_io.p : nullptr;
         L.tile_node = (c->opt_nn_mode == 2) ? (uint32_t*)c->node_io.p : nullptr;
         L.lb_io = (float*)c->lb.p;
-        L.cand_io = (c->opt_nn_mode >= 5) ? (uint4*)c->cand.p : nullptr;
+        L.cand_io = (c->opt_nn_mode == 5 || c->opt_nn_mode == 6) ? (uint4*)c->cand.p : nullptr;
         L.part_a = nullptr;
         L.state = c->d_state;
         L.apply_pending = 1;
@@ -357,9 +379,9 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
             }
         }
         L.init_best = init_best;
-        ICPB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+        ICPB_CUDA(c, cudaEventRecord(c->ev_it[3 * slot], c->stream));
         ICPB_TRY(nn_launch(c, L));
-        ICPB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+        ICPB_CUDA(c, cudaEventRecord(c->ev_it[3 * slot + 1], c->stream));
 
         // stage A: this rank's Chan partial of the distances; ranks exchange partials, every rank merges them in rank order
         PeerMail pm;
@@ -378,21 +400,29 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
                                             (ncclComm_t)c->comm, c->stream));
         // stage B (+ the solve on a single rank)
         ICPB_TRY(stage_b_launch(c, L.sx, L.sy, L.sz, L.pos_out, L.dist_out, n, iter, rank_a,
-                                c->opt_write_mask ? (uint8_t*)c->mask.p : nullptr, part_b, rank_b, p2p ? &pm : nullptr));
+                                c->opt_write_mask ? (uint8_t*)c->mask.p : nullptr, part_b, rank_b, p2p ? &pm : nullptr, c->d_rec + slot));
         if (c->n_ranks > 1 && !p2p) {
             ICPB_NCCL(c, c->nccl->AllGather(rank_b + (size_t)c->rank * STATB_DOUBLES, rank_b, STATB_DOUBLES, ncclFloat64,
                                             (ncclComm_t)c->comm, c->stream));
-            ICPB_TRY(solve_launch(c, rank_b, c->n_ranks));
+            ICPB_TRY(solve_launch(c, rank_b, c->n_ranks, c->d_rec + slot));
         }
-        ICPB_CUDA(c, cudaEventRecord(c->ev[8], c->stream));
-        ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+        ICPB_CUDA(c, cudaEventRecord(c->ev_it[3 * slot + 2], c->stream));
+    }
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int slot = 0; slot < n_batch && go_on; ++slot) {
+        const int iter = iter0 + slot;
+        const IterRecord rec = c->h_rec[slot];
+        if (rec.iteration != iter + 1) {  // cannot happen while go_on: the record of the ending iteration stops the host first
+            c->err = "iteration record missing";
+            return ICP_CUDA_ERROR;
+        }
         float nn_ms = 0.f, iter_ms = 0.f;
-        cudaEventElapsedTime(&nn_ms, c->ev[0], c->ev[1]);
-        cudaEventElapsedTime(&iter_ms, c->ev[0], c->ev[8]);
+        cudaEventElapsedTime(&nn_ms, c->ev_it[3 * slot], c->ev_it[3 * slot + 1]);
+        cudaEventElapsedTime(&iter_ms, c->ev_it[3 * slot], c->ev_it[3 * slot + 2]);
         out->ms_nn_total += nn_ms;
         if (iter == 0) out->ms_nn_first = nn_ms;
-        const IterRecord rec = *c->h_rec;
-        if (c->opt_count && getenv("ICP_B200_DEBUG_ITER")) {  // profiling aid: counters and work-list lengths of this iteration
+        out->loop_iterations = iter + 1;
+        if (debug_iter) {  // profiling aid: counters and work-list lengths of this iteration
             unsigned long long w[8];
             unsigned int wc[16];
             cudaMemcpy(w, c->d_counters, sizeof w, cudaMemcpyDeviceToHost);
@@ -403,7 +433,8 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
             cudaMemset(c->d_counters, 0, sizeof w);
         }
         prev_rmse = rec.rmse;
-        if (!acc.consume(rec, iter, nn_ms, iter_ms, true)) break;
+        if (!acc.consume(rec, iter, nn_ms, iter_ms, true)) go_on = false;
+    }
     }
     ICPB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
 
@@ -411,12 +442,12 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     *write_back = acc.write_back;
     if (acc.write_back)  // the last T, if any
         ICPB_TRY(apply_pending_launch(c, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p, n,
-                                      (c->opt_nn_mode == 5 || phase >= 1) ? (float*)c->lb.p : nullptr,
-                                      (c->opt_nn_mode == 7 && c->lists_valid) ? (float*)c->lb.p : nullptr));
+                                      (c->opt_nn_mode == 5 || phase >= 1) ? (float*)c->lb.p : nullptr));
     if (!c->prev_valid) c->lists_valid = false;
     c->keep_valid = c->prev_valid && acc.write_back && (c->opt_nn_mode == 5 || phase >= 1) && c->opt_temporal_skip;
     c->last_rmse = prev_rmse;
     acc.finish();
+    ICPB_CUDA(c, cudaMemcpyAsync(&c->rmse_build, &c->d_state->rmse_build, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
     {
         float ms = 0.f;
@@ -572,7 +603,9 @@ int icp_create(icp_handle* out, int device_id) {
     if (cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long));
     if (cudaMalloc(&c->d_work_count, 16 * sizeof(unsigned int)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
-    if (cudaHostAlloc(&c->h_rec, sizeof(IterRecord), cudaHostAllocMapped) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    if (cudaHostAlloc(&c->h_rec, Ctx::REC_RING * sizeof(IterRecord), cudaHostAllocMapped) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    for (auto& e : c->ev_it)
+        if (cudaEventCreate(&e) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaHostGetDevicePointer(&c->d_rec, c->h_rec, 0) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (getenv("ICP_B200_DEBUG_COUNTERS")) c->opt_count = true;
     const char* m = getenv("ICP_B200_NN_MODE");
@@ -591,7 +624,7 @@ void icp_destroy(icp_handle h) {
     c->workers.clear();
     octree_free(c);
     DevBuf* bufs[] = {&c->tgt_raw, &c->sx, &c->sy, &c->sz, &c->sperm, &c->pos, &c->dist, &c->mask, &c->part_a, &c->part_b,
-                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt, &c->lb, &c->cand, &c->work2, &c->gstart, &c->lhdr, &c->lcand, &c->lpos};
+                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt, &c->lb, &c->cand, &c->work2, &c->gstart, &c->lhdr, &c->lcand, &c->lpos, &c->gidx, &c->gflag};
     for (DevBuf* b : bufs) devbuf_free(*b);
     if (c->pin_a.p) cudaFreeHost(c->pin_a.p);
     if (c->pin_b.p) cudaFreeHost(c->pin_b.p);
@@ -600,6 +633,8 @@ void icp_destroy(icp_handle h) {
     if (c->d_work_count) cudaFree(c->d_work_count);
     if (c->h_rec) cudaFreeHost(c->h_rec);
     for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_it)
         if (e) cudaEventDestroy(e);
     if (c->ev_src) cudaEventDestroy(c->ev_src);
     if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -682,7 +717,9 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     else if (!strcmp(key, "box_guess")) c->opt_box_guess = std::min(std::max(value, 0.01), 4.0);
     else if (!strcmp(key, "box_emax")) c->opt_box_emax = std::min(std::max(value, 0.01), 8.0);
     else if (!strcmp(key, "box_skin")) { c->opt_box_skin = std::min(std::max(value, 0.0), 2.0); c->lists_valid = false; }
+    else if (!strcmp(key, "lookahead")) c->opt_lookahead = std::min(std::max((int)value, 1), Ctx::REC_RING);
     else if (!strcmp(key, "box_lists")) { c->opt_box_lists = value != 0.0; c->lists_valid = false; }
+    else if (!strcmp(key, "box_rebuild")) c->opt_box_rebuild = std::min(std::max(value, 0.0), 1.0);
     else if (!strcmp(key, "box_tighten")) c->opt_box_tighten = std::min(std::max(value, -1.0), 8.0);
     else {
         c->err = std::string("unknown option ") + key;

@@ -994,10 +994,12 @@ __global__ void __launch_bounds__(256) group_cell_flag_kernel(const uint64_t* __
 }
 
 __global__ void __launch_bounds__(256) group_scatter_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ excl,
-                                                            int64_t n, uint32_t* __restrict__ start) {
+                                                            int64_t n, uint32_t* __restrict__ start, uint32_t* __restrict__ ordinal) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (flag[i]) start[excl[i]] = (uint32_t)i;
+    const uint32_t f = flag[i], e = excl[i];
+    if (f) start[e] = (uint32_t)i;
+    if (ordinal) ordinal[i] = e + f - 1u;  // the run element i belongs to
 }
 
 __global__ void __launch_bounds__(256) group_split_kernel(uint32_t* __restrict__ flag, const uint32_t* __restrict__ excl,
@@ -1009,8 +1011,10 @@ __global__ void __launch_bounds__(256) group_split_kernel(uint32_t* __restrict__
     flag[i] = (f || (within % (uint32_t)QGROUP_MAX) == 0u) ? 1u : 0u;
 }
 
-__global__ void __launch_bounds__(256) group_fixed_kernel(uint32_t* __restrict__ gstart, int64_t n_groups, int64_t n) {
+__global__ void __launch_bounds__(256) group_fixed_kernel(uint32_t* __restrict__ gstart, uint32_t* __restrict__ gidx, int64_t n_groups,
+                                                          int64_t n) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) gidx[g] = (uint32_t)(g / QGROUP_MAX);
     if (g > n_groups) return;
     gstart[g] = (uint32_t)min(g * QGROUP_MAX, n);
 }
@@ -1019,7 +1023,8 @@ __global__ void __launch_bounds__(256) group_fixed_kernel(uint32_t* __restrict__
 int make_fixed_groups(Ctx* c, int64_t n) {
     const int64_t ng = (n + QGROUP_MAX - 1) / QGROUP_MAX;
     ICPB_TRY(devbuf_reserve(c, c->gstart, (size_t)(ng + 1) * sizeof(uint32_t)));
-    group_fixed_kernel<<<(int)((ng + 1 + 255) / 256), 256, 0, c->stream>>>((uint32_t*)c->gstart.p, ng, n);
+    ICPB_TRY(devbuf_reserve(c, c->gidx, (size_t)std::max<int64_t>(n, 1) * sizeof(uint32_t)));
+    group_fixed_kernel<<<(int)((std::max(n, ng + 1) + 255) / 256), 256, 0, c->stream>>>((uint32_t*)c->gstart.p, (uint32_t*)c->gidx.p, ng, n);
     c->launches++;
     c->n_groups = ng;
     c->groups_n = n;
@@ -1035,13 +1040,14 @@ static int make_cell_groups(Ctx* c, const uint64_t* keys, int64_t n, int shift, 
     cudaStream_t s = c->stream;
     const int kb = (int)((n + 255) / 256);
     ICPB_TRY(devbuf_reserve(c, c->gstart, (size_t)(n + 1) * sizeof(uint32_t)));
+    ICPB_TRY(devbuf_reserve(c, c->gidx, (size_t)n * sizeof(uint32_t)));
     uint32_t* d_total = (uint32_t*)c->part_a.p + 8;  // (part_a holds at least 4 KB once a tree was built; reserved below otherwise)
     group_cell_flag_kernel<<<kb, 256, 0, s>>>(keys, n, shift, flag);
     ICPB_TRY(exclusive_scan_u32(c, flag, excl, n, nullptr));
-    group_scatter_kernel<<<kb, 256, 0, s>>>(flag, excl, n, cell_start);
+    group_scatter_kernel<<<kb, 256, 0, s>>>(flag, excl, n, cell_start, nullptr);
     group_split_kernel<<<kb, 256, 0, s>>>(flag, excl, cell_start, n);
     ICPB_TRY(exclusive_scan_u32(c, flag, excl, n, d_total));
-    group_scatter_kernel<<<kb, 256, 0, s>>>(flag, excl, n, (uint32_t*)c->gstart.p);
+    group_scatter_kernel<<<kb, 256, 0, s>>>(flag, excl, n, (uint32_t*)c->gstart.p, (uint32_t*)c->gidx.p);
     c->launches += 4;
     uint32_t total = 0;
     ICPB_CUDA(c, cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, s));

@@ -102,6 +102,10 @@ struct Ctx {
     int64_t groups_n = -1;     // number of source slots the groups cover (-1: none built)
     CellGrid cg;
     DevBuf lhdr, lcand, lpos;  // carried candidate lists of the groups (nn_box.cu); c->lb holds the per-query distance bounds
+    DevBuf gidx, gflag;        // group of each query; per group, the epoch of the last rebuild request
+    unsigned int box_epoch = 0;
+    double rmse_build = 0.0;   // RMSE at the last complete build of the lists (LoopState::rmse_build, carried between runs)
+    double opt_box_rebuild = 0.35;   // mode 7: all lists are rebuilt when the RMSE falls below this fraction of its value at the last build
     bool lists_valid = false;  // the lists and bounds describe the resident source as it is now, against the current target
     bool opt_box_lists = true;       // mode 7: carry the groups' candidate lists from one iteration to the next
     double opt_box_skin = 0.15;      // mode 7: skin added to the balls when a list is built, in cells of the cell grid
@@ -145,8 +149,12 @@ struct Ctx {
     unsigned int mail_epoch = 0;
     unsigned long long* d_counters = nullptr;  // see NNArgs::counters (4 entries)
     unsigned int* d_work_count = nullptr;      // mode 4/5: lengths of the two work lists (node_io, work2)
-    IterRecord* h_rec = nullptr;  // pinned, device-mapped
+    IterRecord* h_rec = nullptr;  // pinned, device-mapped: ring of REC_RING records, one per iteration enqueued ahead
     IterRecord* d_rec = nullptr;
+    static constexpr int REC_RING = 8;
+    cudaEvent_t ev_it[3 * REC_RING] = {};  // per ring slot: NN stage begins / NN stage ends / iteration ends
+    int opt_lookahead = 4;           // iterations enqueued before the host looks at the records (1 when a callback, a stop flag
+                                     // or a host-side per-iteration decision needs every record as it is produced)
 
     // batch of small registrations: pool of worker handles (own stream each) on this device
     std::vector<Ctx*> workers;

@@ -29,10 +29,8 @@ __device__ __forceinline__ StatA stat_empty() {
     return s;
 }
 
-// Distances -> per-block Chan partials -> (last block) this rank's partial.  Each thread owns a fixed set of
-// elements and the merges follow a fixed tree, so the result does not depend on scheduling.
+// Welford update == stat_merge(a, {1, d, 0}) (the stage API's kernel below; the loop's own pass does not divide per element)
 __device__ __forceinline__ void stat_push(StatA& a, double d) {
-    // Welford update == stat_merge(a, {1, d, 0})
     a.n += 1.0;
     const double delta = d - a.mean;
     a.mean += delta / a.n;
@@ -55,21 +53,90 @@ __device__ __forceinline__ StatA stat_block_merge(StatA acc, StatA* sm /* RED_TH
     return sm[0];
 }
 
+// Distances -> this rank's (count, mean, M2, min, max, problems), streaming at memory speed: every thread keeps the pivoted
+// moments  s1 = sum (d - p),  s2 = sum (d - p)^2  of a fixed set of elements (p = last iteration's mean, 0 at the first: no
+// division per element and no cancellation in  M2 = s2 - s1^2 / n  once p is near the mean), the block adds them in a fixed
+// shuffle tree, the last block adds the block partials in index order.  mean = p + s1 / n.  Independent of scheduling.
+struct MomA {
+    double n, s1, s2, dmin, dmax, problems;
+};
+
+__device__ __forceinline__ void moma_push(MomA& a, double d, double p) {
+    const double t = d - p;
+    a.s1 += t;
+    a.s2 += t * t;
+    if (isfinite(d)) {
+        a.dmin = fmin(a.dmin, d);
+        a.dmax = fmax(a.dmax, d);
+    } else {
+        a.problems += 1.0;
+    }
+}
+
+__device__ __forceinline__ MomA moma_add(const MomA& a, const MomA& b) {
+    MomA r;
+    r.n = a.n + b.n;
+    r.s1 = a.s1 + b.s1;
+    r.s2 = a.s2 + b.s2;
+    r.dmin = fmin(a.dmin, b.dmin);
+    r.dmax = fmax(a.dmax, b.dmax);
+    r.problems = a.problems + b.problems;
+    return r;
+}
+
+__device__ __forceinline__ MomA moma_block_sum(MomA v, MomA* sm /* RED_THREADS / 32 */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MomA w;
+        w.n = __shfl_xor_sync(0xffffffffu, v.n, o);
+        w.s1 = __shfl_xor_sync(0xffffffffu, v.s1, o);
+        w.s2 = __shfl_xor_sync(0xffffffffu, v.s2, o);
+        w.dmin = __shfl_xor_sync(0xffffffffu, v.dmin, o);
+        w.dmax = __shfl_xor_sync(0xffffffffu, v.dmax, o);
+        w.problems = __shfl_xor_sync(0xffffffffu, v.problems, o);
+        v = moma_add(v, w);  // commutative term by term: every lane ends with the same bits
+    }
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    MomA r = sm[0];
+#pragma unroll
+    for (int w = 1; w < RED_THREADS / 32; ++w) r = moma_add(r, sm[w]);
+    __syncthreads();
+    return r;
+}
+
 __global__ void __launch_bounds__(RED_THREADS) stat_a_kernel(const double* __restrict__ dist, int64_t n,
-                                                             StatA* __restrict__ part, unsigned int* __restrict__ ticket,
+                                                             StatA* __restrict__ part, LoopState* __restrict__ st,
                                                              StatA* __restrict__ rank_slot, const PeerMail pm) {
-    __shared__ StatA sm[RED_THREADS];
+    __shared__ MomA sm[RED_THREADS / 32];
     __shared__ bool is_last;
-    // block-contiguous chunk, thread-strided inside it (coalesced, fixed assignment)
+    if (st->exit_code != 0) return;  // the loop has ended: iterations enqueued ahead of the host's knowledge do nothing
+    const double p = isfinite(st->mean) ? st->mean : 0.0;
+    // block-contiguous chunk, thread-strided inside it (coalesced, fixed assignment), four loads in flight
     const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
     const int64_t b = (int64_t)blockIdx.x * chunk, e = min(n, b + chunk);
-    StatA acc = stat_empty();
-    for (int64_t i = b + threadIdx.x; i < e; i += RED_THREADS) stat_push(acc, dist[i]);
-    const StatA tot = stat_block_merge(acc, sm);
+    MomA acc;
+    acc.n = 0.0; acc.s1 = 0.0; acc.s2 = 0.0; acc.dmin = DBL_MAX; acc.dmax = 0.0; acc.problems = 0.0;
+    int64_t i = b + threadIdx.x;
+    for (; i + 3 * RED_THREADS < e; i += 4 * RED_THREADS) {
+        const double d0 = dist[i], d1 = dist[i + RED_THREADS], d2 = dist[i + 2 * RED_THREADS], d3 = dist[i + 3 * RED_THREADS];
+        moma_push(acc, d0, p);
+        moma_push(acc, d1, p);
+        moma_push(acc, d2, p);
+        moma_push(acc, d3, p);
+        acc.n += 4.0;
+    }
+    for (; i < e; i += RED_THREADS) {
+        moma_push(acc, dist[i], p);
+        acc.n += 1.0;
+    }
+    const MomA tot = moma_block_sum(acc, sm);
+    MomA* mpart = reinterpret_cast<MomA*>(part);
     if (threadIdx.x == 0) {
-        part[blockIdx.x] = tot;
+        mpart[blockIdx.x] = tot;
         __threadfence();
-        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        is_last = atomicAdd(&st->ticket_a, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (!is_last) return;
@@ -77,12 +144,26 @@ __global__ void __launch_bounds__(RED_THREADS) stat_a_kernel(const double* __res
     const int n_part = (int)gridDim.x;
     const int per = (n_part + RED_THREADS - 1) / RED_THREADS;
     const int pb = threadIdx.x * per, pe = min(n_part, pb + per);
-    StatA a2 = stat_empty();
-    for (int k = pb; k < pe; ++k) a2 = stat_merge(a2, stat_load_cg(part + k));
-    const StatA all = stat_block_merge(a2, sm);
+    MomA a2;
+    a2.n = 0.0; a2.s1 = 0.0; a2.s2 = 0.0; a2.dmin = DBL_MAX; a2.dmax = 0.0; a2.problems = 0.0;
+    for (int k = pb; k < pe; ++k) {
+        const double* q = reinterpret_cast<const double*>(mpart + k);
+        MomA v;
+        v.n = __ldcg(q); v.s1 = __ldcg(q + 1); v.s2 = __ldcg(q + 2); v.dmin = __ldcg(q + 3); v.dmax = __ldcg(q + 4); v.problems = __ldcg(q + 5);
+        a2 = moma_add(a2, v);
+    }
+    const MomA all_m = moma_block_sum(a2, sm);
+    StatA all;
+    all.n = all_m.n;
+    all.mean = all_m.n > 0.0 ? p + all_m.s1 / all_m.n : 0.0;
+    all.m2 = all_m.n > 0.0 ? fmax(all_m.s2 - all_m.s1 * (all_m.s1 / all_m.n), 0.0) : 0.0;
+    if (!(all.m2 == all.m2)) all.m2 = all_m.s2;  // inf - inf: keep the infinity the reference would carry
+    all.dmin = all_m.dmin;
+    all.dmax = all_m.dmax;
+    all.problems = all_m.problems;
     if (threadIdx.x == 0) {
         *rank_slot = all;
-        *ticket = 0u;
+        st->ticket_a = 0u;
     }
     if (pm.epoch && threadIdx.x < pm.n_ranks) {
         // this rank's record into every rank's mailbox (its own included), then the epoch: one thread per destination
@@ -102,7 +183,7 @@ int stat_a_launch(Ctx* c, const double* dist, int64_t n, StatA* part, StatA* ran
     none.epoch = 0u;
     none.n_ranks = 1;
     none.rank = 0;
-    stat_a_kernel<<<stat_a_blocks(c, n), RED_THREADS, 0, c->stream>>>(dist, n, part, &c->d_state->ticket_a, rank_slot, pm ? *pm : none);
+    stat_a_kernel<<<stat_a_blocks(c, n), RED_THREADS, 0, c->stream>>>(dist, n, part, c->d_state, rank_slot, pm ? *pm : none);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
     return ICP_OK;
@@ -250,6 +331,7 @@ __global__ void __launch_bounds__(RED_THREADS, 2) stage_b_kernel(const double* _
     __shared__ double s_rb[MAIL_RANKS * STATB_DOUBLES];
     __shared__ double sm_red[RED_THREADS];
     __shared__ bool is_last;
+    if (st->exit_code != 0) return;  // the loop has ended: iterations enqueued ahead of the host's knowledge do nothing
     StatA a_all;
     double mean = 0.0, sd = 0.0;
     if (threadIdx.x == 0) {
@@ -406,14 +488,15 @@ int stage_b_blocks(Ctx* c, int64_t n) {
 }
 
 int stage_b_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const uint32_t* pos, const double* dist,
-                   int64_t n, int iter, const StatA* rank_a, uint8_t* mask_out, double* part, double* rank_b, const PeerMail* pm) {
+                   int64_t n, int iter, const StatA* rank_a, uint8_t* mask_out, double* part, double* rank_b, const PeerMail* pm,
+                   IterRecord* rec) {
     PeerMail none;
     none.epoch = 0u;
     none.n_ranks = 1;
     none.rank = 0;
     const int blocks = stage_b_blocks(c, n);
     stage_b_kernel<<<blocks, RED_THREADS, 0, c->stream>>>(sx, sy, sz, pos, dist, n, c->fast.pts, c->d_state, rank_a, c->n_ranks,
-                                                          c->rank, iter, mask_out, part, rank_b, c->d_rec, pm ? *pm : none);
+                                                          c->rank, iter, mask_out, part, rank_b, rec ? rec : c->d_rec, pm ? *pm : none);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
     return ICP_OK;
@@ -431,11 +514,12 @@ int pairs_b_launch(Ctx* c, const double* a_xyz, const double* b_xyz, int64_t n, 
 __global__ void solve_kernel(LoopState* __restrict__ st, const double* __restrict__ rank_parts, int n_ranks,
                              IterRecord* __restrict__ rec) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st->exit_code != 0) return;  // the loop has ended
     solve_step(st, rank_parts, n_ranks, rec);
 }
 
-int solve_launch(Ctx* c, const double* rank_parts, int n_ranks) {
-    solve_kernel<<<1, 32, 0, c->stream>>>(c->d_state, rank_parts, n_ranks, c->d_rec);
+int solve_launch(Ctx* c, const double* rank_parts, int n_ranks, IterRecord* rec) {
+    solve_kernel<<<1, 32, 0, c->stream>>>(c->d_state, rank_parts, n_ranks, rec ? rec : c->d_rec);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
     return ICP_OK;

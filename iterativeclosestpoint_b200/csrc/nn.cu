@@ -83,7 +83,6 @@ __device__ __forceinline__ void nn_one_query(const NNArgs& A, const long long i,
     A.pos_out[i] = pos;
     if (A.node_io && !A.worklist) A.node_io[i] = result_node;
     A.dist_out[i] = d;
-    if (A.ebound) A.ebound[i] = __double2float_ru(d);
     st.n = 1.0;
     st.mean = d;
     if (isfinite(d)) {
@@ -99,6 +98,7 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
     __shared__ StatA warp_part[NN_THREADS / 32];
     const long long i = (long long)blockIdx.x * NN_THREADS + threadIdx.x;
     uint2* stk = stack + threadIdx.x;
+    if (A.state && A.state->exit_code != 0) return;  // the loop has ended: iterations enqueued ahead do nothing
 
     StatA st;
     st.n = 0.0; st.mean = 0.0; st.m2 = 0.0; st.dmin = DBL_MAX; st.dmax = 0.0; st.problems = 0.0;
@@ -205,9 +205,12 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
     A.lhdr = nullptr;
     A.lcand = nullptr;
     A.lpos = nullptr;
-    A.ebound = nullptr;
+    A.list_final = 0;
     A.group_list = nullptr;
     A.group_count = nullptr;
+    A.gidx = (const uint32_t*)c->gidx.p;
+    A.gflag = (unsigned int*)c->gflag.p;
+    A.epoch = 0u;
     A.sx = L.sx; A.sy = L.sy; A.sz = L.sz;
     A.ox = L.ox; A.oy = L.oy; A.oz = L.oz;
     A.n = L.n;
@@ -236,25 +239,26 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
     if (L.mode == 7) {
         // box search over the query groups; the per-thread kernel (cell walk, then climb / literal) takes what it leaves
         const bool in_place = !L.apply_pending || (L.ox == L.sx && L.oy == L.sy && L.oz == L.sz);
-        if (c->cg.valid && c->gstart.p && c->n_groups > 0 && L.n == c->groups_n && in_place && c->d_work_count && c->node_io.p) {
+        const bool lists = c->lhdr.p && c->lcand.p && c->lpos.p && c->work2.p && c->gidx.p && c->gflag.p;
+        if (lists && c->cg.valid && c->gstart.p && c->n_groups > 0 && L.n == c->groups_n && in_place && c->d_work_count && c->node_io.p) {
             ICPB_CUDA(c, cudaMemsetAsync(c->d_work_count, 0, 2 * sizeof(unsigned int), c->stream));
             A.worklist = (uint32_t*)c->node_io.p;
             A.work_count = c->d_work_count;
             A.node_io = nullptr;
             A.lb_io = nullptr;
-            // carried lists: only inside a registration over the resident source (the caller says so by passing the bounds)
-            const bool lists = c->opt_box_lists && L.lb_io && in_place && c->lhdr.p && c->lcand.p && c->lpos.p && c->work2.p;
-            if (lists) {
+            {
                 A.lhdr = (BoxListHdr*)c->lhdr.p;
                 A.lcand = (float4*)c->lcand.p;
                 A.lpos = (uint32_t*)c->lpos.p;
-                A.ebound = L.lb_io;
                 A.group_list = (uint32_t*)c->work2.p;
                 A.group_count = c->d_work_count + 1;
+                if (++c->box_epoch == 0u) ++c->box_epoch;  // (0 = the flags' initial value)
+                A.epoch = c->box_epoch;
+                // the lists are carried from one iteration to the next inside a registration over the resident source
+                const bool with_lists = c->opt_box_lists && c->lists_valid && L.prev_pos && L.apply_pending && L.state;
+                ICPB_TRY(nn_box_launch(c, A, with_lists));
+                c->lists_valid = L.state != nullptr && L.apply_pending;  // every group now carries a list built for where its queries are
             }
-            const bool with_lists = lists && c->lists_valid && L.prev_pos && L.apply_pending;
-            ICPB_TRY(nn_box_launch(c, A, with_lists));
-            if (lists) c->lists_valid = true;  // either way every group now carries a header and every query a bound
             A.mode = 3;
             A.gbias = c->opt_walk_bias != -100 ? c->opt_walk_bias : -2;
             A.gbias_mul = std::ldexp(1.0, -A.gbias);

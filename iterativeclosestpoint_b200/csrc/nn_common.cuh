@@ -85,9 +85,12 @@ struct NNArgs {
     BoxListHdr* lhdr;          // carried lists (may be null: none are kept)
     float4* lcand;
     uint32_t* lpos;
-    float* ebound;             // per query: upper bound of the distance to its current match (FP32, rounded up)
+    int list_final;            // nn_list_kernel: queries the list cannot settle go to the per-thread kernel (no rebuild request)
     uint32_t* group_list;      // groups nn_list_kernel leaves to the builder ...
     unsigned int* group_count; // ... and how many
+    const uint32_t* __restrict__ gidx;  // group of each query
+    unsigned int* gflag;       // per group: epoch of the iteration that last asked for a rebuild
+    unsigned int epoch;
 };
 
 struct NodeRegs {
