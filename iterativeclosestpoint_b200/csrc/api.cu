@@ -2,7 +2,6 @@
 // (replaces ICPEngine::registerPointClouds / runICP, core/icpengine.cpp:24-60,117-394, and the CLI's ICP(),
 // icp_registration.cpp:443-622) and the sharded multi-GPU driver.
 #include "internal.h"
-#include "nn_common.cuh"
 #include <nccl.h>
 #include <dlfcn.h>
 #include <cmath>
@@ -31,7 +30,7 @@ int pairs_b_launch(Ctx* c, const double* a_xyz, const double* b_xyz, int64_t n, 
 int solve_launch(Ctx* c, const double* rank_parts, int n_ranks, IterRecord* rec = nullptr);
 int bestfit_launch(Ctx* c, const double* b17, const double* a0, const double* b0, double* T_out);
 int solve_from_H_launch(Ctx* c, const double* in15, double* out37);
-int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n, float* lb = nullptr, float* eb = nullptr);
+int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n, float* lb = nullptr);
 int unsort_results_launch(Ctx* c, const uint32_t* pos, const double* dist, const uint32_t* perm, int64_t n, int32_t* idx_out,
                           double* dist_out);
 int aos_to_soa_launch(Ctx* c, const double* xyz, int64_t n, double* sx, double* sy, double* sz);
@@ -108,18 +107,9 @@ static int ensure_run_buffers(Ctx* c, int64_t n) {
     ICPB_TRY(devbuf_reserve(c, c->mask, (size_t)n));
     ICPB_TRY(devbuf_reserve(c, c->node_io, (size_t)n * sizeof(uint32_t)));
     ICPB_TRY(devbuf_reserve(c, c->lb, (size_t)n * sizeof(float)));
-    if (c->opt_nn_mode == 5 || c->opt_nn_mode == 6) ICPB_TRY(devbuf_reserve(c, c->cand, (size_t)n * sizeof(uint4)));
-    if (c->opt_nn_mode >= 5) ICPB_TRY(devbuf_reserve(c, c->work2, (size_t)n * sizeof(uint32_t)));
-    if (c->opt_nn_mode == 7 && c->groups_n == n && c->n_groups > 0) {  // carried candidate lists of the query groups (nn_box.cu)
-        ICPB_TRY(devbuf_reserve(c, c->lhdr, (size_t)c->n_groups * sizeof(BoxListHdr)));
-        ICPB_TRY(devbuf_reserve(c, c->lcand, (size_t)c->n_groups * BOX_LIST_CAP * sizeof(float4)));
-        ICPB_TRY(devbuf_reserve(c, c->lpos, (size_t)c->n_groups * BOX_LIST_CAP * sizeof(uint32_t)));
-        const size_t had = c->gflag.cap;
-        ICPB_TRY(devbuf_reserve(c, c->gflag, (size_t)c->n_groups * sizeof(unsigned int)));
-        if (c->gflag.cap != had) {  // fresh storage: no group has asked for a rebuild in any epoch yet
-            ICPB_CUDA(c, cudaMemsetAsync(c->gflag.p, 0, c->gflag.cap, c->stream));
-            c->box_epoch = 0u;
-        }
+    if (c->opt_nn_mode >= 5) {
+        ICPB_TRY(devbuf_reserve(c, c->cand, (size_t)n * sizeof(uint4)));
+        ICPB_TRY(devbuf_reserve(c, c->work2, (size_t)n * sizeof(uint32_t)));
     }
     const size_t nbA = (size_t)std::max<int64_t>(stat_a_blocks(c, n), (n + 255) / 256 / 4) + 1024;
     ICPB_TRY(devbuf_reserve(c, c->part_a, nbA * sizeof(StatA)));
@@ -168,7 +158,6 @@ static int source_from_device_aos(Ctx* c, const double* d_xyz, int64_t n) {
     if (c->opt_order_queries && n > 1)
         return order_queries(c, d_xyz, n, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p, (uint32_t*)c->sperm.p);
     c->src_identity_perm = true;
-    ICPB_TRY(make_fixed_groups(c, n));
     return aos_to_soa_launch(c, d_xyz, n, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p);
 }
 
@@ -286,8 +275,6 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     hs.variant = variant;
     hs.max_iterations = P.max_iterations;
     hs.n_global = n_global;
-    hs.rebuild_ratio = c->opt_box_rebuild;
-    hs.rmse_build = (c->prev_valid && c->lists_valid && c->opt_nn_mode == 7) ? c->rmse_build : 0.0;
     ICPB_CUDA(c, cudaMemcpyAsync(c->d_state, &hs, sizeof hs, cudaMemcpyHostToDevice, c->stream));
 
     RunAcc acc(c, out, variant, P.max_iterations, (long long)n_global);
@@ -303,7 +290,6 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
 
     const bool resume = c->prev_valid;  // same resident source and tree as the last run: its matches seed this one
     c->prev_valid = false;
-    if (!resume || c->opt_nn_mode != 7) c->lists_valid = false;
     if (c->opt_nn_mode == 2 && !resume)  // per-tile start nodes: the root until a tile has searched once
         ICPB_CUDA(c, cudaMemsetAsync(c->node_io.p, 0, (size_t)((n + 31) / 32) * sizeof(uint32_t), c->stream));
     if (c->opt_nn_mode == 4)  // temporal bounds belong to one run: the source moves between runs
@@ -328,7 +314,7 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     // every record as it is produced (the reference calls back and polls stop() once per iteration, icpengine.cpp:160-164,364-367).
     const bool debug_iter = c->opt_count && getenv("ICP_B200_DEBUG_ITER");
     const bool each = stop_flag || c->on_iteration || c->on_progress || c->on_log || debug_iter ||
-                      !(c->opt_nn_mode == 0 || c->opt_nn_mode == 1 || c->opt_nn_mode == 3 || c->opt_nn_mode == 7);
+                      !(c->opt_nn_mode == 0 || c->opt_nn_mode == 1 || c->opt_nn_mode == 3);
     const int ahead = each ? 1 : std::min(std::max(c->opt_lookahead, 1), (int)Ctx::REC_RING);
     bool go_on = true;
     for (int iter0 = 0; iter0 < P.max_iterations && go_on; iter0 += ahead) {
@@ -355,7 +341,7 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         L.node_io = (c->opt_nn_mode == 1) ? (uint32_t*)c->node_io.p : nullptr;
         L.tile_node = (c->opt_nn_mode == 2) ? (uint32_t*)c->node_io.p : nullptr;
         L.lb_io = (float*)c->lb.p;
-        L.cand_io = (c->opt_nn_mode == 5 || c->opt_nn_mode == 6) ? (uint4*)c->cand.p : nullptr;
+        L.cand_io = (c->opt_nn_mode >= 5) ? (uint4*)c->cand.p : nullptr;
         L.part_a = nullptr;
         L.state = c->d_state;
         L.apply_pending = 1;
@@ -443,11 +429,9 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     if (acc.write_back)  // the last T, if any
         ICPB_TRY(apply_pending_launch(c, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p, n,
                                       (c->opt_nn_mode == 5 || phase >= 1) ? (float*)c->lb.p : nullptr));
-    if (!c->prev_valid) c->lists_valid = false;
     c->keep_valid = c->prev_valid && acc.write_back && (c->opt_nn_mode == 5 || phase >= 1) && c->opt_temporal_skip;
     c->last_rmse = prev_rmse;
     acc.finish();
-    ICPB_CUDA(c, cudaMemcpyAsync(&c->rmse_build, &c->d_state->rmse_build, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
     {
         float ms = 0.f;
@@ -609,7 +593,7 @@ int icp_create(icp_handle* out, int device_id) {
     if (cudaHostGetDevicePointer(&c->d_rec, c->h_rec, 0) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (getenv("ICP_B200_DEBUG_COUNTERS")) c->opt_count = true;
     const char* m = getenv("ICP_B200_NN_MODE");
-    if (m) c->opt_nn_mode = std::min(std::max(atoi(m), 0), 7);
+    if (m) c->opt_nn_mode = std::min(std::max(atoi(m), 0), 6);
     *out = (icp_handle)c;
     return ICP_OK;
 }
@@ -624,7 +608,7 @@ void icp_destroy(icp_handle h) {
     c->workers.clear();
     octree_free(c);
     DevBuf* bufs[] = {&c->tgt_raw, &c->sx, &c->sy, &c->sz, &c->sperm, &c->pos, &c->dist, &c->mask, &c->part_a, &c->part_b,
-                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt, &c->lb, &c->cand, &c->work2, &c->gstart, &c->lhdr, &c->lcand, &c->lpos, &c->gidx, &c->gflag};
+                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt, &c->lb, &c->cand, &c->work2};
     for (DevBuf* b : bufs) devbuf_free(*b);
     if (c->pin_a.p) cudaFreeHost(c->pin_a.p);
     if (c->pin_b.p) cudaFreeHost(c->pin_b.p);
@@ -687,7 +671,7 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     Ctx* c = (Ctx*)h;
     if (!c || !key) return ICP_INVALID_ARGUMENT;
     if (!strcmp(key, "nn_mode")) {
-        c->opt_nn_mode = std::min(std::max((int)(value + 0.5), 0), 7);
+        c->opt_nn_mode = std::min(std::max((int)(value + 0.5), 0), 6);
         c->prev_valid = false;
     }
     else if (!strcmp(key, "count")) c->opt_count = value != 0.0;
@@ -714,13 +698,7 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     else if (!strcmp(key, "keep_rcap")) c->opt_keep_rcap = std::min(std::max(value, 0.0), 8.0);
     else if (!strcmp(key, "keep_bias")) c->opt_keep_bias = std::min(std::max((int)value, -4), 4);
     else if (!strcmp(key, "write_mask")) c->opt_write_mask = value != 0.0;
-    else if (!strcmp(key, "box_guess")) c->opt_box_guess = std::min(std::max(value, 0.01), 4.0);
-    else if (!strcmp(key, "box_emax")) c->opt_box_emax = std::min(std::max(value, 0.01), 8.0);
-    else if (!strcmp(key, "box_skin")) { c->opt_box_skin = std::min(std::max(value, 0.0), 2.0); c->lists_valid = false; }
     else if (!strcmp(key, "lookahead")) c->opt_lookahead = std::min(std::max((int)value, 1), Ctx::REC_RING);
-    else if (!strcmp(key, "box_lists")) { c->opt_box_lists = value != 0.0; c->lists_valid = false; }
-    else if (!strcmp(key, "box_rebuild")) c->opt_box_rebuild = std::min(std::max(value, 0.0), 1.0);
-    else if (!strcmp(key, "box_tighten")) c->opt_box_tighten = std::min(std::max(value, -1.0), 8.0);
     else {
         c->err = std::string("unknown option ") + key;
         return ICP_INVALID_ARGUMENT;
@@ -943,7 +921,6 @@ int icp_iteration_stats(icp_handle h, const double* src_xyz, int64_t n, const in
     ICPB_CUDA(c, cudaSetDevice(c->device));
     ICPB_TRY(build_inv_perm(c));
     c->prev_valid = false;
-    c->lists_valid = false;
     ICPB_TRY(upload(c, c->scratch_src, src_xyz, n));
     ICPB_TRY(ensure_source_buffers(c, n));
     ICPB_TRY(ensure_run_buffers(c, n));

@@ -549,8 +549,6 @@ static void tree_free(DeviceOctree& t) {
 void octree_free(Ctx* c) {
     tree_free(c->tree);
     tree_free(c->fast);
-    if (c->cg.cells) cudaFree(c->cg.cells);
-    c->cg = CellGrid();
 }
 
 static int grow_nodes(Ctx* c, DeviceOctree& t, int64_t need) {
@@ -583,8 +581,7 @@ static int grow_nodes(Ctx* c, DeviceOctree& t, int64_t need) {
 // cloud's bounding box, octree.cpp:41-126).  cubic == true: the SEARCH tree -- same construction over a cubic root,
 // so its cells are cubes; it only has to bound its points (every point lies in the closed box of its leaf), not
 // to match anything in the reference.
-static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, int max_pts, int max_depth, bool cubic,
-                      const uint64_t** sorted_keys_out = nullptr) {
+static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, int max_pts, int max_depth, bool cubic) {
     tree_reset(t);  // keeps the device allocations of an earlier build (grow-only), forgets its contents
     t.want_cell = cubic;
     t.max_pts = max_pts;
@@ -679,7 +676,6 @@ static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, i
         t.root_hi[a] = root[3 + a];
     }
     t.valid = true;
-    if (sorted_keys_out) *sorted_keys_out = keys;  // in c->scratch1, valid until its next user
     return ICP_OK;
 }
 
@@ -861,79 +857,21 @@ static int build_grid(Ctx* c, DeviceOctree& t) {
     return ICP_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Cell grid of the box search (nn_box.cu): one dense level over the cloud's bounding box, entry = the contiguous range of the
-// cell's points in the search tree's point order.  Built straight from the sorted cell-path keys: the first point of a run
-// of equal level-L prefixes writes the range's begin, the last one its end.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) cell_grid_fill_kernel(const uint64_t* __restrict__ keys, int64_t m, int shift, int level,
-                                                             int nx, int ny, int nz, uint2* __restrict__ cells) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const uint64_t k = keys[i] >> shift;
-    const bool first = i == 0 || (keys[i - 1] >> shift) != k;
-    const bool last = i + 1 == m || (keys[i + 1] >> shift) != k;
-    if (!first && !last) return;
-    uint32_t x = 0, y = 0, z = 0;  // de-interleave: octant bit 0 = x, 1 = y, 2 = z, most significant level first
-    for (int l = 0; l < level; ++l) {
-        const uint32_t o = (uint32_t)(k >> (3 * l)) & 7u;
-        x |= (o & 1u) << l;
-        y |= ((o >> 1) & 1u) << l;
-        z |= ((o >> 2) & 1u) << l;
-    }
-    if (x >= (uint32_t)nx || y >= (uint32_t)ny || z >= (uint32_t)nz) return;  // cannot happen: the box covers the cloud
-    uint2* e = cells + ((int64_t)z * ny + y) * nx + x;
-    if (first) e->x = (uint32_t)i;
-    if (last) e->y = (uint32_t)(i + 1);
-}
-
-static int build_cell_grid(Ctx* c, const DeviceOctree& t, const uint64_t* sorted_keys, int key_levels) {
-    CellGrid& g = c->cg;
-    g.valid = false;
-    if (t.glev_n <= 0 || !sorted_keys) return ICP_OK;
-    // the base level of the pyramid: the deepest level whose occupied cells still hold several points (build_grid)
-    const int k = t.gbase;
-    g.level = std::min(t.glev_min + k, key_levels);
-    if (g.level != t.glev_min + k) return ICP_OK;  // (a depth cap below the base level: the box search is not offered)
-    for (int a = 0; a < 3; ++a) g.dim[a] = t.gdim[k][a];
-    g.edge = t.cube / (double)(1ll << g.level);
-    g.inv = (double)(1ll << g.level) / t.cube;
-    const int64_t total = (int64_t)g.dim[0] * g.dim[1] * g.dim[2];
-    if (g.cap < total) {
-        if (g.cells) ICPB_CUDA(c, cudaFree(g.cells));
-        g.cells = nullptr;
-        g.cap = 0;
-        ICPB_CUDA(c, cudaMalloc(&g.cells, (size_t)total * sizeof(uint2)));
-        g.cap = total;
-    }
-    ICPB_CUDA(c, cudaMemsetAsync(g.cells, 0, (size_t)total * sizeof(uint2), c->stream));
-    cell_grid_fill_kernel<<<(int)((t.n_pts + 255) / 256), 256, 0, c->stream>>>(sorted_keys, t.n_pts, 3 * (key_levels - g.level), g.level,
-                                                                             g.dim[0], g.dim[1], g.dim[2], g.cells);
-    c->launches++;
-    ICPB_CUDA(c, cudaGetLastError());
-    g.valid = true;
-    return ICP_OK;
-}
-
 // The reference's tree (c->tree: structure parity, literal traversal) and the isotropic search tree (c->fast: every
 // fast search path, and the canonical point order that match positions refer to).
 int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int max_depth) {
     c->tree.valid = false;
     c->fast.valid = false;
     c->prev_valid = false;
-    c->lists_valid = false;
     if (m <= 0) return ICP_EMPTY_INPUT;
     if (max_depth < 0 || max_depth > 21 || m > 0x7fffffffLL) {
         c->err = "octree: max_depth must be in [0,21] and n_tgt < 2^31";
         return ICP_INVALID_ARGUMENT;
     }
     ICPB_TRY(build_tree(c, c->tree, d_xyz, m, max_pts, max_depth, false));
-    const uint64_t* fast_keys = nullptr;
-    c->cg.valid = false;
-    ICPB_TRY(build_tree(c, c->fast, d_xyz, m, c->opt_search_leaf, c->opt_search_depth, true, &fast_keys));
+    ICPB_TRY(build_tree(c, c->fast, d_xyz, m, c->opt_search_leaf, c->opt_search_depth, true));
     ICPB_TRY(build_inv_perm_of(c, c->fast));  // original index -> search-tree position (literal results, stage API)
     ICPB_TRY(build_grid(c, c->fast));
-    ICPB_TRY(build_cell_grid(c, c->fast, fast_keys, c->opt_search_depth));  // the keys are still in scratch1
     return ICP_OK;
 }
 
@@ -942,32 +880,31 @@ int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int
 // nodes.  Queries are ordered by a 3x21-bit Morton code of their own bounding box (this is only a
 // permutation for locality -- any order gives the same per-query answer).
 // ------------------------------------------------------------------------------------------------
-// 13 bits per axis at least (8192^3 cells: centimetres on a 100 m tile, ~0.4 m on a 3 km one) order the queries finely enough
-// for neighbouring threads to share cells, and keep the sort at 5 radix passes instead of 8.
+// 13 bits per axis (8192^3 cells: centimetres on a 100 m tile, ~0.4 m on a 3 km one) order the queries finely enough for
+// neighbouring threads to share cells, and keep the sort at 5 radix passes instead of 8.
 constexpr int QKEY_BITS = 13;
-constexpr int QGROUP_MAX = 8;  // queries per group (nn_box.cu: one quarter-warp per group)
+constexpr uint32_t QKEY_MAX = (1u << QKEY_BITS) - 1u;
 
 __global__ void __launch_bounds__(256) query_keys_kernel(const double* __restrict__ xyz, int64_t n,
-                                                         const double* __restrict__ box, int bits, uint64_t* __restrict__ keys,
+                                                         const double* __restrict__ box, uint64_t* __restrict__ keys,
                                                          uint32_t* __restrict__ idx) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    // ISOTROPIC cells: one scale (the largest extent) for all three axes, so that consecutive queries form a
+    // ISOTROPIC cells: one scale (the largest extent) for all three axes, so that 32 consecutive queries form a
     // compact, roughly cubic clump (a per-axis scale would slice 2.5-D scenes into thin height slabs whose tiles
     // follow contour lines).
-    const uint32_t qmax = (1u << bits) - 1u;
     const double ext = fmax(fmax(box[3] - box[0], box[4] - box[1]), box[5] - box[2]);
-    const double inv = ext > 0.0 ? (double)(1u << bits) / ext : 0.0;
+    const double inv = ext > 0.0 ? (double)QKEY_MAX / ext : 0.0;
     uint64_t key = 0;
     uint32_t q[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         double f = (xyz[3 * i + a] - box[a]) * inv;
         if (!(f > 0.0)) f = 0.0;  // also catches NaN
-        if (f > (double)qmax) f = (double)qmax;
+        if (f > (double)QKEY_MAX) f = (double)QKEY_MAX;
         q[a] = (uint32_t)f;
     }
-    for (int b = bits - 1; b >= 0; --b)
+    for (int b = QKEY_BITS - 1; b >= 0; --b)
         key = (key << 3) | (((q[0] >> b) & 1u)) | (((q[1] >> b) & 1u) << 1) | (((q[2] >> b) & 1u) << 2);
     keys[i] = key;
     idx[i] = (uint32_t)i;
@@ -985,121 +922,27 @@ __global__ void __launch_bounds__(256) gather_soa_kernel(const double* __restric
     perm[i] = j;
 }
 
-// ---- groups: runs of at most QGROUP_MAX consecutive queries of one cell (key prefix) ----
-__global__ void __launch_bounds__(256) group_cell_flag_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift,
-                                                              uint32_t* __restrict__ flag) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    flag[i] = (i == 0 || (keys[i] >> shift) != (keys[i - 1] >> shift)) ? 1u : 0u;
-}
-
-__global__ void __launch_bounds__(256) group_scatter_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ excl,
-                                                            int64_t n, uint32_t* __restrict__ start, uint32_t* __restrict__ ordinal) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t f = flag[i], e = excl[i];
-    if (f) start[e] = (uint32_t)i;
-    if (ordinal) ordinal[i] = e + f - 1u;  // the run element i belongs to
-}
-
-__global__ void __launch_bounds__(256) group_split_kernel(uint32_t* __restrict__ flag, const uint32_t* __restrict__ excl,
-                                                          const uint32_t* __restrict__ cell_start, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t f = flag[i];
-    const uint32_t within = (uint32_t)i - cell_start[excl[i] + f - 1u];
-    flag[i] = (f || (within % (uint32_t)QGROUP_MAX) == 0u) ? 1u : 0u;
-}
-
-__global__ void __launch_bounds__(256) group_fixed_kernel(uint32_t* __restrict__ gstart, uint32_t* __restrict__ gidx, int64_t n_groups,
-                                                          int64_t n) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < n) gidx[g] = (uint32_t)(g / QGROUP_MAX);
-    if (g > n_groups) return;
-    gstart[g] = (uint32_t)min(g * QGROUP_MAX, n);
-}
-
-// groups of QGROUP_MAX consecutive slots (sources kept in caller order)
-int make_fixed_groups(Ctx* c, int64_t n) {
-    const int64_t ng = (n + QGROUP_MAX - 1) / QGROUP_MAX;
-    ICPB_TRY(devbuf_reserve(c, c->gstart, (size_t)(ng + 1) * sizeof(uint32_t)));
-    ICPB_TRY(devbuf_reserve(c, c->gidx, (size_t)std::max<int64_t>(n, 1) * sizeof(uint32_t)));
-    group_fixed_kernel<<<(int)((std::max(n, ng + 1) + 255) / 256), 256, 0, c->stream>>>((uint32_t*)c->gstart.p, (uint32_t*)c->gidx.p, ng, n);
-    c->launches++;
-    c->n_groups = ng;
-    c->groups_n = n;
-    c->lists_valid = false;
-    ICPB_CUDA(c, cudaGetLastError());
-    return ICP_OK;
-}
-
-// sorted keys -> c->gstart / c->n_groups.  `shift`: key bits below the grouping cell's prefix (>= 64: no cells, fixed runs).
-// flag / excl / cell_start: n uint32 of scratch each.
-static int make_cell_groups(Ctx* c, const uint64_t* keys, int64_t n, int shift, uint32_t* flag, uint32_t* excl, uint32_t* cell_start) {
-    if (shift >= 64) return make_fixed_groups(c, n);
-    cudaStream_t s = c->stream;
-    const int kb = (int)((n + 255) / 256);
-    ICPB_TRY(devbuf_reserve(c, c->gstart, (size_t)(n + 1) * sizeof(uint32_t)));
-    ICPB_TRY(devbuf_reserve(c, c->gidx, (size_t)n * sizeof(uint32_t)));
-    uint32_t* d_total = (uint32_t*)c->part_a.p + 8;  // (part_a holds at least 4 KB once a tree was built; reserved below otherwise)
-    group_cell_flag_kernel<<<kb, 256, 0, s>>>(keys, n, shift, flag);
-    ICPB_TRY(exclusive_scan_u32(c, flag, excl, n, nullptr));
-    group_scatter_kernel<<<kb, 256, 0, s>>>(flag, excl, n, cell_start, nullptr);
-    group_split_kernel<<<kb, 256, 0, s>>>(flag, excl, cell_start, n);
-    ICPB_TRY(exclusive_scan_u32(c, flag, excl, n, d_total));
-    group_scatter_kernel<<<kb, 256, 0, s>>>(flag, excl, n, (uint32_t*)c->gstart.p, (uint32_t*)c->gidx.p);
-    c->launches += 4;
-    uint32_t total = 0;
-    ICPB_CUDA(c, cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, s));
-    ICPB_CUDA(c, cudaStreamSynchronize(s));
-    const uint32_t n32 = (uint32_t)n;
-    ICPB_CUDA(c, cudaMemcpyAsync((uint32_t*)c->gstart.p + total, &n32, sizeof n32, cudaMemcpyHostToDevice, s));
-    c->n_groups = total;
-    c->groups_n = n;
-    c->lists_valid = false;
-    ICPB_CUDA(c, cudaGetLastError());
-    return ICP_OK;
-}
-
 int order_queries(Ctx* c, const double* d_q, int64_t n, double* sx, double* sy, double* sz, uint32_t* perm) {
     cudaStream_t s = c->stream;
     const int bb_blocks = (int)std::min<int64_t>((n + BBOX_THREADS - 1) / BBOX_THREADS, (int64_t)c->sm_count * 8);
     ICPB_TRY(devbuf_reserve(c, c->scratch0, (size_t)(bb_blocks + 1) * 6 * sizeof(double) + 64));
-    ICPB_TRY(devbuf_reserve(c, c->part_a, 4096));
     double* d_part = (double*)c->scratch0.p;
     double* d_box = d_part + (size_t)bb_blocks * 6;
-    // With a target in place the queries are ordered over ITS cubic root, so that a group's queries start out inside one cell
-    // of the cell grid (nn_box.cu); without one, over their own bounding box.
-    int bits = QKEY_BITS, shift = 64;
-    if (c->fast.valid && c->cg.valid) {
-        bits = std::min(std::max(c->cg.level + 3, QKEY_BITS), 16);
-        shift = 3 * (bits - c->cg.level);
-        double box[6];
-        for (int a = 0; a < 3; ++a) {
-            box[a] = c->fast.root_lo[a];
-            box[3 + a] = c->fast.root_lo[a] + c->fast.cube;
-        }
-        ICPB_CUDA(c, cudaMemcpyAsync(d_box, box, sizeof box, cudaMemcpyHostToDevice, s));
-    } else {
-        bbox_partial_kernel<<<bb_blocks, BBOX_THREADS, 0, s>>>(d_q, n, d_part);
-        bbox_finish_kernel<<<1, 192, 0, s>>>(d_part, bb_blocks, d_q, d_box);
-        c->launches += 2;
-    }
+    bbox_partial_kernel<<<bb_blocks, BBOX_THREADS, 0, s>>>(d_q, n, d_part);
+    bbox_finish_kernel<<<1, 192, 0, s>>>(d_part, bb_blocks, d_q, d_box);
     ICPB_TRY(devbuf_reserve(c, c->scratch1, (size_t)n * (2 * sizeof(uint64_t) + 2 * sizeof(uint32_t)) + 1024));
     uint64_t* keys = (uint64_t*)c->scratch1.p;
     uint64_t* keys_alt = keys + n;
     uint32_t* idx = (uint32_t*)(keys_alt + n);
     uint32_t* idx_alt = idx + n;
     const int kb = (int)((n + 255) / 256);
-    query_keys_kernel<<<kb, 256, 0, s>>>(d_q, n, d_box, bits, keys, idx);
-    c->launches++;
-    ICPB_TRY(radix_sort_pairs(c, keys, keys_alt, idx, idx_alt, n, 3 * bits));
+    query_keys_kernel<<<kb, 256, 0, s>>>(d_q, n, d_box, keys, idx);
+    c->launches += 3;
+    ICPB_TRY(radix_sort_pairs(c, keys, keys_alt, idx, idx_alt, n, 3 * QKEY_BITS));
     gather_soa_kernel<<<kb, 256, 0, s>>>(d_q, idx, n, sx, sy, sz, perm);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
-    // free now: the sort's other key buffer and, once the gather has consumed the permutation, both index buffers
-    uint32_t* c_region = (uint32_t*)((uint64_t*)c->scratch1.p + 2 * n);
-    return make_cell_groups(c, keys, n, shift, c_region, c_region + n, (uint32_t*)keys_alt);
+    return ICP_OK;
 }
 
 int build_inv_perm(Ctx* c) { return build_inv_perm_of(c, c->fast); }

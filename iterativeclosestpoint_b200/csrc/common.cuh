@@ -103,10 +103,6 @@ struct LoopState {
     int variant, max_iterations;
     long long n_global;  // N of mean / variance (global source size)
     unsigned int ticket_a, ticket_b;
-    // nn_box.cu: candidate lists are rebuilt (tighter) when the RMSE has fallen below `rebuild_ratio` x its value at the last
-    // complete build; the list kernel of the next iteration reads `rebuild_all`
-    double rmse_build, rebuild_ratio;
-    int rebuild_all;
 };
 
 // Host-visible record written once per iteration by the solve step.

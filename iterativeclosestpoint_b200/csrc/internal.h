@@ -35,18 +35,6 @@ struct DeviceOctree {
     bool valid = false;
 };
 
-// Plain dense cell grid over the search tree's cubic root at ONE level (nn_box.cu): entry = [first, one past last) position
-// of the cell's points in the search tree's point order (the points are sorted by their full-depth cell path, so the points
-// of any cell at any level are contiguous whatever the node table looks like).  (0, 0) = empty cell.
-struct CellGrid {
-    uint2* cells = nullptr;
-    int64_t cap = 0;
-    int level = 0;
-    int dim[3] = {0, 0, 0};
-    double edge = 0.0, inv = 0.0;
-    bool valid = false;
-};
-
 // Reusable device buffer that only grows.
 struct DevBuf {
     void* p = nullptr;
@@ -95,21 +83,6 @@ struct Ctx {
     // resident source in internal (query-coherent) order
     DevBuf sx, sy, sz, sperm;  // SoA coordinates + original index of each internal slot
     int64_t n_src = 0;
-    // nn_box.cu: the internal order is cut into GROUPS of at most 8 consecutive queries that share one cell of the cell grid
-    // (at ordering time); gstart[g] = first internal slot of group g, gstart[n_groups] = n_src
-    DevBuf gstart;
-    int64_t n_groups = 0;
-    int64_t groups_n = -1;     // number of source slots the groups cover (-1: none built)
-    CellGrid cg;
-    DevBuf lhdr, lcand, lpos;  // carried candidate lists of the groups (nn_box.cu); c->lb holds the per-query distance bounds
-    DevBuf gidx, gflag;        // group of each query; per group, the epoch of the last rebuild request
-    unsigned int box_epoch = 0;
-    double rmse_build = 0.0;   // RMSE at the last complete build of the lists (LoopState::rmse_build, carried between runs)
-    double opt_box_rebuild = 0.35;   // mode 7: all lists are rebuilt when the RMSE falls below this fraction of its value at the last build
-    bool lists_valid = false;  // the lists and bounds describe the resident source as it is now, against the current target
-    bool opt_box_lists = true;       // mode 7: carry the groups' candidate lists from one iteration to the next
-    double opt_box_skin = 0.15;      // mode 7: skin added to the balls when a list is built, in cells of the cell grid
-    double opt_box_tighten = 0.45;   // mode 7: slack (in cells) above which a list is rebuilt tighter; 0 = never
     DevBuf pos, dist, mask;    // per-query NN result (sorted target position), distance, inlier mask
     DevBuf node_io;            // per-query leaf of the last match (temporal start of the next search); mode 4: the work list
     DevBuf lb;                 // mode 4: per-query lower bound on the distance to every non-matched target point (float)
@@ -131,11 +104,8 @@ struct Ctx {
     bool prev_valid = false;         // pos / node_io hold last run's matches of the resident source against the current tree
     float last_build_ms = 0.f;
     // tuning knobs (icp_set_option)
-    int opt_nn_mode = 7;             // 0: literal traversal from the root; 1: climb; 2: warp tiles; 3: cell walk; 4: balanced cell walk;
-                                     // 5: keep / collect (nn_keep.cu); 6: 4 while the registration moves, 5 once it has nearly converged;
-                                     // 7: box search (nn_box.cu), the per-thread cell walk over its work list
-    double opt_box_guess = 0.6;      // mode 7: half box edge for a query without a previous match, in cells of the cell grid
-    double opt_box_emax = 1.0;       // mode 7: widest ball the box search takes, in cells
+    int opt_nn_mode = 6;             // 0: literal traversal from the root; 1: climb; 2: warp tiles; 3: cell walk; 4: balanced cell walk;
+                                     // 5: keep / collect (nn_keep.cu); 6: 4 while the registration moves, 5 once it has nearly converged
     bool opt_order_queries = true;   // Morton-order the source for traversal coherence
     bool opt_write_mask = false;     // keep the per-point inlier mask of the last iteration
     bool opt_count = false;          // maintain the NN path counters (same-address atomics: profiling / tests only)
@@ -154,7 +124,7 @@ struct Ctx {
     static constexpr int REC_RING = 8;
     cudaEvent_t ev_it[3 * REC_RING] = {};  // per ring slot: NN stage begins / NN stage ends / iteration ends
     int opt_lookahead = 4;           // iterations enqueued before the host looks at the records (1 when a callback, a stop flag
-                                     // or a host-side per-iteration decision needs every record as it is produced)
+                                     // or the per-iteration debug counters need every record as it is produced)
 
     // batch of small registrations: pool of worker handles (own stream each) on this device
     std::vector<Ctx*> workers;
@@ -196,7 +166,6 @@ int exclusive_scan_u32(Ctx* c, const uint32_t* d_in, uint32_t* d_out, int64_t n,
 // permutation (internal slot -> original index).
 int order_queries(Ctx* c, const double* d_q_xyz, int64_t n, double* sx, double* sy, double* sz, uint32_t* perm);
 int build_inv_perm(Ctx* c);
-int make_fixed_groups(Ctx* c, int64_t n);  // c->gstart / c->n_groups for a source kept in caller order
 
 // nn.cu
 struct NNLaunch {

@@ -575,7 +575,7 @@ __device__ __forceinline__ void apply_T(const double* T, double& x, double& y, d
 // applies state->T_pending if state->have_T (used once at loop exit)
 __global__ void __launch_bounds__(256) apply_pending_kernel(const LoopState* __restrict__ st, double* __restrict__ x,
                                                             double* __restrict__ y, double* __restrict__ z, int64_t n,
-                                                            float* __restrict__ lb, float* __restrict__ eb) {
+                                                            float* __restrict__ lb) {
     if (!st->have_T) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -588,10 +588,6 @@ __global__ void __launch_bounds__(256) apply_pending_kernel(const LoopState* __r
     if (lb) {  // nn_keep.cu: the bound holds for where the point was; it moved by at most this much
         const double moved = dmul(dsqrt(sumsq3(dsub(a, oa), dsub(b, ob), dsub(c, oc))), 1.0 + 1e-9);
         lb[i] = __double2float_rd(dsub((double)lb[i], moved));
-    }
-    if (eb) {  // nn_box.cu: the match is at most this much farther away from where the point is now
-        const double moved = dmul(dsqrt(sumsq3(dsub(a, oa), dsub(b, ob), dsub(c, oc))), 1.0 + 1e-9);
-        eb[i] = __double2float_ru(dadd((double)eb[i], moved));
     }
 }
 
@@ -642,8 +638,8 @@ __global__ void __launch_bounds__(256) aos_to_soa_kernel(const double* __restric
 
 static inline int nblk(int64_t n) { return (int)((n + 255) / 256); }
 
-int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n, float* lb, float* eb) {
-    if (n > 0) apply_pending_kernel<<<nblk(n), 256, 0, c->stream>>>(c->d_state, x, y, z, n, lb, eb);
+int apply_pending_launch(Ctx* c, double* x, double* y, double* z, int64_t n, float* lb) {
+    if (n > 0) apply_pending_kernel<<<nblk(n), 256, 0, c->stream>>>(c->d_state, x, y, z, n, lb);
     clear_pending_kernel<<<1, 32, 0, c->stream>>>(c->d_state);
     c->launches += 2;
     ICPB_CUDA(c, cudaGetLastError());

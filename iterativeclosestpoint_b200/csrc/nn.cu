@@ -153,7 +153,6 @@ int nn_tile_launch(Ctx* c, const NNArgs& A);   // nn_tile.cu
 int nn_group_launch(Ctx* c, const NNArgs& A);  // nn_group.cu
 int nn_group_lean_launch(Ctx* c, const NNArgs& A);  // nn_group_lean.cu
 int nn_keep_launch(Ctx* c, const NNArgs& A, int k);  // nn_keep.cu
-int nn_box_launch(Ctx* c, const NNArgs& A, bool with_lists);  // nn_box.cu
 
 int nn_launch(Ctx* c, const NNLaunch& L_in) {
     NNLaunch L = L_in;
@@ -190,27 +189,6 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
         for (int a = 0; a < 3; ++a) mag = std::max(mag, std::max(std::fabs(c->fast.root_lo[a]), std::fabs(c->fast.root_hi[a])));
         A.geps += 64.0 * 2.220446049250313e-16 * mag;
     }
-    A.cells = c->cg.cells;
-    for (int a = 0; a < 3; ++a) A.cdim[a] = c->cg.dim[a];
-    A.cinv = c->cg.inv;
-    A.gstart = (const uint32_t*)c->gstart.p;
-    A.n_groups = c->n_groups;
-    A.cinv_lo = std::nextafterf((float)c->cg.inv, 0.0f);
-    A.cinv_hi = std::nextafterf((float)c->cg.inv, INFINITY);
-    A.box_guess = c->opt_box_guess * c->cg.edge;
-    A.box_emax = c->opt_box_emax * c->cg.edge;
-    A.box_skin = c->opt_box_skin * c->cg.edge;
-    A.box_tighten = (float)(c->opt_box_tighten * c->cg.edge);
-    A.geps2_f = std::nextafterf((float)(2.0 * A.geps), INFINITY);
-    A.lhdr = nullptr;
-    A.lcand = nullptr;
-    A.lpos = nullptr;
-    A.list_final = 0;
-    A.group_list = nullptr;
-    A.group_count = nullptr;
-    A.gidx = (const uint32_t*)c->gidx.p;
-    A.gflag = (unsigned int*)c->gflag.p;
-    A.epoch = 0u;
     A.sx = L.sx; A.sy = L.sy; A.sz = L.sz;
     A.ox = L.ox; A.oy = L.oy; A.oz = L.oz;
     A.n = L.n;
@@ -236,43 +214,6 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
     A.walk_alpha = std::max(c->opt_keep_alpha, 1.0);
     A.walk_wmul = std::ldexp(2.0, -c->opt_keep_bias);
     A.walk_rcap = c->opt_keep_rcap * A.gedge[A.gbase];
-    if (L.mode == 7) {
-        // box search over the query groups; the per-thread kernel (cell walk, then climb / literal) takes what it leaves
-        const bool in_place = !L.apply_pending || (L.ox == L.sx && L.oy == L.sy && L.oz == L.sz);
-        const bool lists = c->lhdr.p && c->lcand.p && c->lpos.p && c->work2.p && c->gidx.p && c->gflag.p;
-        if (lists && c->cg.valid && c->gstart.p && c->n_groups > 0 && L.n == c->groups_n && in_place && c->d_work_count && c->node_io.p) {
-            ICPB_CUDA(c, cudaMemsetAsync(c->d_work_count, 0, 2 * sizeof(unsigned int), c->stream));
-            A.worklist = (uint32_t*)c->node_io.p;
-            A.work_count = c->d_work_count;
-            A.node_io = nullptr;
-            A.lb_io = nullptr;
-            {
-                A.lhdr = (BoxListHdr*)c->lhdr.p;
-                A.lcand = (float4*)c->lcand.p;
-                A.lpos = (uint32_t*)c->lpos.p;
-                A.group_list = (uint32_t*)c->work2.p;
-                A.group_count = c->d_work_count + 1;
-                if (++c->box_epoch == 0u) ++c->box_epoch;  // (0 = the flags' initial value)
-                A.epoch = c->box_epoch;
-                // the lists are carried from one iteration to the next inside a registration over the resident source
-                const bool with_lists = c->opt_box_lists && c->lists_valid && L.prev_pos && L.apply_pending && L.state;
-                ICPB_TRY(nn_box_launch(c, A, with_lists));
-                c->lists_valid = L.state != nullptr && L.apply_pending;  // every group now carries a list built for where its queries are
-            }
-            A.mode = 3;
-            A.gbias = c->opt_walk_bias != -100 ? c->opt_walk_bias : -2;
-            A.gbias_mul = std::ldexp(1.0, -A.gbias);
-            A.apply_pending = 0;
-            nn_kernel<<<std::min(nn_grid_blocks(L.n), c->sm_count * 16), NN_THREADS, 0, c->stream>>>(A);
-            c->launches++;
-            ICPB_CUDA(c, cudaGetLastError());
-            return ICP_OK;
-        }
-        L.mode = 3;
-        A.mode = 3;
-        A.gbias = c->opt_walk_bias != -100 ? c->opt_walk_bias : -2;
-        A.gbias_mul = std::ldexp(1.0, -A.gbias);
-    }
     if (L.mode == 2) return nn_tile_launch(c, A);
     const bool in_place5 = L.ox == L.sx && L.oy == L.sy && L.oz == L.sz;
     if (L.mode == 5 && L.prev_pos && A.lb_io && L.cand_io && in_place5 && L.apply_pending && c->d_work_count && c->node_io.p && c->work2.p) {

@@ -10,17 +10,6 @@ constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr int SEED_SCAN = 8;                // points inspected to seed a query
 #define ICPB_INF __longlong_as_double(0x7FF0000000000000LL)
 
-// Carried candidate list of one query group (nn_box.cu): header + BOX_LIST_CAP slots of (x, y, z, |p|^2) relative to the box
-// centre and of sorted-target positions.  count == 0xFFFFFFFF: no list (too many candidates, or the group is not searchable).
-constexpr int BOX_LIST_CAP = 96;
-struct __align__(16) BoxListHdr {
-    double og[3];
-    float hf[3];
-    uint32_t count;
-    uint32_t pad[2];
-};
-static_assert(sizeof(BoxListHdr) == 48, "BoxListHdr layout (nn_list_kernel reads it as three 16-byte words)");
-
 struct NNArgs {
     const Node* __restrict__ nodes;    // search tree (isotropic cells): every fast path; match positions index `pts`
     const TPoint* __restrict__ pts;
@@ -70,27 +59,6 @@ struct NNArgs {
     unsigned int* work_count;  // ... and how many; the per-thread kernel runs over that list when worklist != null
     double init_best;
     uint32_t pos_of_idx0;
-    // box search (nn_box.cu): the plain cell grid (build.cu) and the query groups
-    const uint2* __restrict__ cells;
-    int cdim[3];
-    double cinv;
-    const uint32_t* __restrict__ gstart;
-    long long n_groups;
-    float cinv_lo, cinv_hi;    // cinv rounded down / up to FP32
-    double box_guess;          // half box edge tried for a query without a previous match
-    double box_emax;           // queries whose ball is wider go to the per-thread search
-    double box_skin;           // added to a seeded query's ball when a list is built: the list stays valid while the query moves
-    float box_tighten;         // a list whose box exceeds every query's ball by more than this is rebuilt (0: never)
-    float geps2_f;             // 2 geps, rounded up
-    BoxListHdr* lhdr;          // carried lists (may be null: none are kept)
-    float4* lcand;
-    uint32_t* lpos;
-    int list_final;            // nn_list_kernel: queries the list cannot settle go to the per-thread kernel (no rebuild request)
-    uint32_t* group_list;      // groups nn_list_kernel leaves to the builder ...
-    unsigned int* group_count; // ... and how many
-    const uint32_t* __restrict__ gidx;  // group of each query
-    unsigned int* gflag;       // per group: epoch of the iteration that last asked for a rebuild
-    unsigned int epoch;
 };
 
 struct NodeRegs {

@@ -260,17 +260,6 @@ static __device__ __noinline__ void solve_step(LoopState* st, const double* rank
             st->pivot_b[r] = cB[r];
         }
     }
-    // candidate lists (nn_box.cu): built wide at the first iteration (seedless balls), then again whenever the registration has
-    // closed in enough for tighter lists to pay
-    if (st->rmse_build <= 0.0) {
-        st->rebuild_all = 1;
-        st->rmse_build = rmse > 0.0 ? rmse : -1.0;
-    } else if (rmse < st->rmse_build * st->rebuild_ratio) {
-        st->rebuild_all = 1;
-        st->rmse_build = rmse;
-    } else {
-        st->rebuild_all = 0;
-    }
     st->exit_code = exit_code;
     rec->iteration = st->iter + 1;
     rec->valid_points = (int)valid;

@@ -38,7 +38,7 @@ def test_octree_and_nn_match_reference_vectors(handle, name, make, leaf, depth):
         qsets["ties"] = clouds.lattice_tie_queries(tgt)
     for variant, tag in ((VARIANT_ENGINE, "engine"), (VARIANT_CLI, "cli")):
         handle.set_params(ICPParameters(octreeMaxPoints=leaf, octreeMaxDepth=depth), variant)
-        for mode in (0, 1, 2, 3, 7):
+        for mode in (0, 1, 2, 3):
             handle.set_option("nn_mode", mode)
             for qname, q in qsets.items():
                 key = f"nn_{tag}_{qname}"
@@ -48,7 +48,7 @@ def test_octree_and_nn_match_reference_vectors(handle, name, make, leaf, depth):
                 assert np.array_equal(idx, g[key]), f"{name}/{qname}/{tag}/mode{mode}"
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5, 6, 7], ids=["climb", "tile", "walk", "group", "keep", "auto", "box"])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5, 6], ids=["climb", "tile", "walk", "group", "keep", "auto"])
 @pytest.mark.parametrize("name,make,kw", ENGINE_RUNS, ids=[c[0] for c in ENGINE_RUNS])
 def test_engine_runs_match_reference_vectors(handle, name, make, kw, mode):
     g = load("engine_" + name)

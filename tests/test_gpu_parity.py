@@ -58,7 +58,7 @@ def test_octree_structure_bit_exact(handle, oracle, name, make, leaf, depth):
     assert info.depth == int(want["depth"].max())
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6, 7], ids=["literal", "climb", "tile", "walk", "group", "keep", "auto", "box"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6], ids=["literal", "climb", "tile", "walk", "group", "keep", "auto"])
 @pytest.mark.parametrize("name,make,leaf,depth", TREE_CASES, ids=[c[0] for c in TREE_CASES])
 def test_nn_indices_bit_exact(handle, oracle, name, make, leaf, depth, mode):
     tgt = make()
@@ -76,7 +76,7 @@ def test_nn_indices_bit_exact(handle, oracle, name, make, leaf, depth, mode):
         assert np.array_equal(dist, d), f"{name}/{qname}: distances are not bit-identical"
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6, 7], ids=["literal", "climb", "tile", "walk", "group", "keep", "auto", "box"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6], ids=["literal", "climb", "tile", "walk", "group", "keep", "auto"])
 def test_nn_lattice_ties_follow_reference_traversal_order(handle, oracle, mode):
     """Exactly equidistant candidates: the winner is the first one the reference's DFS visits, not the lowest index."""
     lat = clouds.lattice_exact()
@@ -97,7 +97,7 @@ def test_nn_nonfinite_queries_return_index_zero(handle, oracle):
     q = np.array([[np.nan, 1.0, 1.0], [np.inf, 0.0, 0.0], [1.0, -np.inf, 2.0], [1e300, 1e300, 1e300], [5.0, 5.0, 1.0]])
     handle.octree_build(tgt)
     want = oracle.octree(tgt).find_nearest(q)
-    for mode in (0, 1, 2, 3, 7):
+    for mode in (0, 1, 2, 3):
         handle.set_option("nn_mode", mode)
         idx, _, _ = handle.nn_query(q)
         assert np.array_equal(idx, want)
@@ -110,7 +110,7 @@ def test_nn_cli_variant_initial_best(handle, oracle):
     handle.set_params(ICPParameters(), VARIANT_CLI)
     handle.octree_build(tgt)
     want = oracle.octree(tgt).find_nearest(q, variant=1)
-    for mode in (0, 1, 2, 3, 7):
+    for mode in (0, 1, 2, 3):
         handle.set_option("nn_mode", mode)
         idx, _, _ = handle.nn_query(q)
         assert np.array_equal(idx, want)
@@ -232,7 +232,7 @@ def _check_run(got, want, n_src, tol=REL_E2E):
         assert np.max(np.abs(got.finalT - want.final_t)) <= tol * max(1.0, float(np.max(np.abs(want.final_t))))
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6, 7], ids=["literal", "climb", "tile", "walk", "group", "keep", "auto", "box"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6], ids=["literal", "climb", "tile", "walk", "group", "keep", "auto"])
 def test_register_config1_engine(handle, oracle, mode):
     """BASELINE.json config #1: 10k-point cloud vs transformed + noised copy, 50 / 1e-6 / 3 sigma / 10 / 20."""
     src, tgt = synth.make_test_icp_pair(10000)
@@ -451,20 +451,17 @@ def test_full_size_config3_sample_parity_and_properties(handle, oracle):
     # carried between iterations) must reproduce the one-thread-per-query walk bit for bit -- every index and distance of
     # every iteration feeds the order-deterministic sums behind these numbers
     runs = {}
-    for mode in (3, 6, 7):
+    for mode in (3, 6):
         handle.set_option("nn_mode", mode)
         handle.set_params(ICPParameters(maxIterations=20, tolerance=1e-15))
         work = src.copy()
         runs[mode] = handle.register(work, tgt)
         del work
-    a = runs[3]
-    for m in (6, 7):
-        b = runs[m]
-        assert a.loopIterations == b.loopIterations == 20, m
-        assert np.array_equal(a.cumulativeT, b.cumulativeT), m
-        assert [h.rmse for h in a.iterationHistory] == [h.rmse for h in b.iterationHistory], m
-        assert [h.validPoints for h in a.iterationHistory] == [h.validPoints for h in b.iterationHistory], m
-    b = runs[6]
+    a, b = runs[3], runs[6]
+    assert a.loopIterations == b.loopIterations == 20
+    assert np.array_equal(a.cumulativeT, b.cumulativeT)
+    assert [h.rmse for h in a.iterationHistory] == [h.rmse for h in b.iterationHistory]
+    assert [h.validPoints for h in a.iterationHistory] == [h.validPoints for h in b.iterationHistory]
     assert b.iterationHistory[-1].nnMs < 0.5 * b.iterationHistory[3].nnMs  # the converged iterations take the keep path
 
 
@@ -573,13 +570,13 @@ def test_search_modes_agree_on_clouds_that_are_not_terrain(handle, shape):
     c0 = tgt.mean(0)
     src = np.ascontiguousarray((tgt - c0) @ R.T + c0 + np.array([0.02, -0.015, 0.01]) + rng.normal(scale=0.002, size=tgt.shape))
     runs = {}
-    for mode in (0, 3, 4, 5, 6, 7):
+    for mode in (0, 3, 4, 5, 6):
         handle.set_option("nn_mode", mode)
         handle.set_params(ICPParameters(maxIterations=10, tolerance=1e-15))
         work = src.copy()
         runs[mode] = (handle.register(work, tgt), work)
     a = runs[0][0]
-    for mode in (3, 4, 5, 6, 7):
+    for mode in (3, 4, 5, 6):
         b = runs[mode][0]
         assert b.loopIterations == a.loopIterations and b.success == a.success, (shape, mode)
         assert np.array_equal(b.cumulativeT, a.cumulativeT), (shape, mode)
