@@ -2,7 +2,6 @@
 // (replaces ICPEngine::registerPointClouds / runICP, core/icpengine.cpp:24-60,117-394, and the CLI's ICP(),
 // icp_registration.cpp:443-622) and the sharded multi-GPU driver.
 #include "internal.h"
-#include <nccl.h>
 #include <dlfcn.h>
 #include <cmath>
 #include <cstdio>
@@ -25,7 +24,7 @@ int dist_from_idx_launch(Ctx* c, const double* sx, const double* sy, const doubl
 int stage_b_blocks(Ctx* c, int64_t n);
 int stage_b_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const uint32_t* pos, const double* dist,
                    int64_t n, int iter, const StatA* rank_a, uint8_t* mask_out, double* part, double* rank_b, const PeerMail* pm = nullptr,
-                   IterRecord* rec = nullptr);
+                   IterRecord* rec = nullptr, int stop_req = 0);
 int pairs_b_launch(Ctx* c, const double* a_xyz, const double* b_xyz, int64_t n, double* part, double* out17);
 int solve_launch(Ctx* c, const double* rank_parts, int n_ranks, IterRecord* rec = nullptr);
 int bestfit_launch(Ctx* c, const double* b17, const double* a0, const double* b0, double* T_out);
@@ -39,56 +38,6 @@ int small_batch_run(Ctx* c, const std::vector<int32_t>& which, double* const* sr
                     const double* const* tgt_xyz, const int64_t* n_tgt, std::vector<IterRecord>& recs, int rec_cap,
                     std::vector<int>& n_rec, std::vector<int>& exit_code, std::vector<char>& flagged,
                     const double*& moved_ptr, std::vector<long long>& src_off);
-
-// ------------------------------------------------------------------------------------------------
-// NCCL, resolved at run time so that the library shares the process's already-loaded libnccl.so.2
-// (torch's bundled copy when driven from Python) and has no link-time dependency for 1-GPU users.
-// ------------------------------------------------------------------------------------------------
-struct NcclApi {
-    void* lib = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    const char* (*GetErrorString)(ncclResult_t) = nullptr;
-};
-
-static NcclApi* nccl_load(Ctx* c) {
-    if (c->nccl) return c->nccl;
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    void* lib = nullptr;
-    for (const char* nm : names) {
-        lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-        if (lib) break;
-    }
-    if (!lib) {
-        c->err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
-        return nullptr;
-    }
-    NcclApi* a = new NcclApi();
-    a->lib = lib;
-    a->GetUniqueId = (decltype(a->GetUniqueId))dlsym(lib, "ncclGetUniqueId");
-    a->CommInitRank = (decltype(a->CommInitRank))dlsym(lib, "ncclCommInitRank");
-    a->CommDestroy = (decltype(a->CommDestroy))dlsym(lib, "ncclCommDestroy");
-    a->AllGather = (decltype(a->AllGather))dlsym(lib, "ncclAllGather");
-    a->GetErrorString = (decltype(a->GetErrorString))dlsym(lib, "ncclGetErrorString");
-    if (!a->GetUniqueId || !a->CommInitRank || !a->CommDestroy || !a->AllGather || !a->GetErrorString) {
-        c->err = "libnccl.so.2 lacks a required symbol";
-        delete a;
-        return nullptr;
-    }
-    c->nccl = a;
-    return a;
-}
-
-#define ICPB_NCCL(ctx, call)                                                                   \
-    do {                                                                                       \
-        ncclResult_t r__ = (call);                                                             \
-        if (r__ != ncclSuccess) {                                                              \
-            (ctx)->err = std::string(#call) + ": " + (ctx)->nccl->GetErrorString(r__);         \
-            return ICP_NCCL_ERROR;                                                             \
-        }                                                                                      \
-    } while (0)
 
 // ------------------------------------------------------------------------------------------------
 static void log_msg(Ctx* c, const char* fmt, ...) {
@@ -191,6 +140,13 @@ struct RunAcc {
     // returns true if the loop goes on
     bool consume(const IterRecord& rec, int iter, float nn_ms, float iter_ms, bool notify) {
         out->loop_iterations = iter + 1;
+        if (rec.exit_code == 4) {  // a rank of a sharded run was asked to stop (icpengine.cpp:160-164): nothing of this iteration counts
+            log_msg(c, "registration stopped");
+            out->status = ICP_CANCELLED;
+            out->loop_iterations = iter;
+            write_back = false;
+            return false;
+        }
         if (rec.problems > 0.0) log_msg(c, "warning: %.0f abnormal distance values", rec.problems);
         log_msg(c, "  distance range: min=%.6f, max=%.6f", rec.dmin, rec.dmax);
         log_msg(c, "  distance stats: mean=%.6f, std=%.6f, threshold=%.6f", rec.mean, rec.std_dev, rec.threshold);
@@ -307,6 +263,7 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     // phase 0 walk; 1 walk that also records bounds (the hand-over iteration); 2 keep / collect
     int phase = (c->opt_nn_mode == 6 && keep_state) ? 2 : 0;
     double prev_rmse = (c->opt_nn_mode == 6 && resume) ? c->last_rmse : -1.0;
+    if (c->n_ranks > 1 && ++c->mail_run >= (1u << 20)) c->mail_run = 1u;
     ICPB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     // The device decides when the loop ends (solve_step: LoopState::exit_code); every kernel of an iteration returns at once
     // when it already has.  So the host may enqueue several iterations before it reads their records: no round trip per
@@ -321,7 +278,10 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     const int n_batch = std::min(ahead, P.max_iterations - iter0);
     for (int slot = 0; slot < n_batch; ++slot) {
         const int iter = iter0 + slot;
-        if (variant == ICP_VARIANT_ENGINE && stop_flag && *stop_flag) {  // icpengine.cpp:160-164
+        // A sharded run must leave on every rank in the same iteration: the request travels with the stage-B records instead
+        // (solve_step, exit code 4) -- a rank that broke out here would leave its peers waiting for its records.
+        const int stop_req = (variant == ICP_VARIANT_ENGINE && stop_flag && *stop_flag) ? 1 : 0;
+        if (stop_req && c->n_ranks <= 1) {  // icpengine.cpp:160-164
             log_msg(c, "registration stopped");
             out->status = ICP_CANCELLED;
             acc.write_back = false;
@@ -374,11 +334,12 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         pm.epoch = 0u;
         pm.n_ranks = c->n_ranks;
         pm.rank = c->rank;
-        const bool p2p = c->n_ranks > 1 && c->p2p;
+        const bool p2p = c->n_ranks > 1 && c->p2p && P.max_iterations < 4000;
         if (p2p) {
+            // epoch = (run, iteration): every rank enters a run with the same run number (icp_register_sharded is a collective
+            // call), so a rank that left the previous run early -- an error on its side -- cannot be satisfied by stale flags
             for (int r = 0; r < MAIL_RANKS; ++r) pm.peer[r] = c->peer_mail[r];
-            if (++c->mail_epoch == 0u) ++c->mail_epoch;
-            pm.epoch = c->mail_epoch;
+            pm.epoch = c->mail_run * 4096u + (unsigned int)iter + 1u;
         }
         ICPB_TRY(stat_a_launch(c, L.dist_out, n, part_a, rank_a + c->rank, p2p ? &pm : nullptr));
         if (c->n_ranks > 1 && !p2p)
@@ -386,7 +347,8 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
                                             (ncclComm_t)c->comm, c->stream));
         // stage B (+ the solve on a single rank)
         ICPB_TRY(stage_b_launch(c, L.sx, L.sy, L.sz, L.pos_out, L.dist_out, n, iter, rank_a,
-                                c->opt_write_mask ? (uint8_t*)c->mask.p : nullptr, part_b, rank_b, p2p ? &pm : nullptr, c->d_rec + slot));
+                                c->opt_write_mask ? (uint8_t*)c->mask.p : nullptr, part_b, rank_b, p2p ? &pm : nullptr, c->d_rec + slot,
+                                c->n_ranks > 1 ? stop_req : 0));
         if (c->n_ranks > 1 && !p2p) {
             ICPB_NCCL(c, c->nccl->AllGather(rank_b + (size_t)c->rank * STATB_DOUBLES, rank_b, STATB_DOUBLES, ncclFloat64,
                                             (ncclComm_t)c->comm, c->stream));
@@ -441,13 +403,41 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     return ICP_OK;
 }
 
-static int write_back_source(Ctx* c, double* host_xyz, int64_t n) {
-    ICPB_TRY(devbuf_reserve(c, c->scratch1, (size_t)n * 3 * sizeof(double)));
+// The resident source (internal order) back into the caller's array.  After a spatial redistribution (shard.cu) the rank holds
+// other ranks' points: they first travel home over NVLink.  `n_caller` = points of the caller's array on this rank.
+static int write_back_source(Ctx* c, double* host_xyz, int64_t n_caller) {
+    const int64_t n = c->n_src;  // resident points
+    ICPB_TRY(devbuf_reserve(c, c->scratch1, (size_t)std::max<int64_t>(n, 1) * 3 * sizeof(double)));
     ICPB_TRY(unsort_launch(c, (double*)c->sx.p, (double*)c->sy.p, (double*)c->sz.p,
                            c->src_identity_perm ? nullptr : (uint32_t*)c->sperm.p, n, (double*)c->scratch1.p));
-    ICPB_CUDA(c, cudaMemcpyAsync(host_xyz, c->scratch1.p, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    const double* d_out = (const double*)c->scratch1.p;
+    if (c->rd_active) {
+        if (n_caller != c->rd_n_in) {
+            c->err = "write-back: the caller's array does not have the size of the shard that was uploaded";
+            return ICP_INVALID_ARGUMENT;
+        }
+        ICPB_TRY(devbuf_reserve(c, c->scratch2, (size_t)std::max<int64_t>(n_caller, 1) * 3 * sizeof(double)));
+        ICPB_TRY(redistribute_return(c, (const double*)c->scratch1.p, (double*)c->scratch2.p));
+        d_out = (const double*)c->scratch2.p;
+    } else if (n_caller != n) {
+        c->err = "write-back: size mismatch";
+        return ICP_INVALID_ARGUMENT;
+    }
+    if (n_caller > 0 && host_xyz)
+        ICPB_CUDA(c, cudaMemcpyAsync(host_xyz, d_out, (size_t)n_caller * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
     return ICP_OK;
+}
+
+// Device AoS points of this rank -> resident source; on a sharded handle the ranks first re-deal the points by region.
+static int source_from_shard(Ctx* c, const double* d_xyz, int64_t n) {
+    const double* d_use = d_xyz;
+    int64_t n_use = n;
+    c->rd_active = false;
+    if (c->n_ranks > 1) ICPB_TRY(redistribute_source(c, d_xyz, n, &d_use, &n_use));
+    c->n_src = n_use;
+    if (n_use <= 0) return ICP_OK;
+    return source_from_device_aos(c, d_use, n_use);
 }
 
 static void init_result(icp_result* out) {
@@ -491,7 +481,10 @@ static int register_impl(Ctx* c, double* src_xyz, int64_t n_src, int64_t n_src_g
     log_msg(c, "target: %lld points", (long long)n_tgt);
 
     ICPB_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
-    ICPB_TRY(stage_cloud(c, c->stream, c->tgt_raw, c->las_tgt, tgt_xyz, tgt_las, n_tgt));
+    if (c->n_ranks > 1 && c->comm && c->opt_shard_target && tgt_xyz && !tgt_las)
+        ICPB_TRY(target_upload_sharded(c, tgt_xyz, n_tgt));  // 1/R of it over this rank's PCIe link, the rest over NVLink
+    else
+        ICPB_TRY(stage_cloud(c, c->stream, c->tgt_raw, c->las_tgt, tgt_xyz, tgt_las, n_tgt));
     c->n_tgt = n_tgt;
     // the source goes up on a second stream so that (from pinned memory) its copy overlaps the target's tree build
     DevBuf& src_stage = c->scratch_src;
@@ -509,16 +502,14 @@ static int register_impl(Ctx* c, double* src_xyz, int64_t n_src, int64_t n_src_g
             c->tree.depth);
     c->src_identity_perm = false;
     c->n_src = n_src;
-    if (n_src > 0) {
-        ICPB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_src, 0));
-        ICPB_TRY(source_from_device_aos(c, (const double*)src_stage.p, n_src));
-    }
+    if (n_src > 0) ICPB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_src, 0));
+    if (n_src > 0 || c->n_ranks > 1) ICPB_TRY(source_from_shard(c, (const double*)src_stage.p, n_src));  // (collective on a sharded handle)
     ICPB_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
 
     bool write_back = true;
     ICPB_TRY(run_loop(c, n_src_global, out, stop_flag, &write_back));
     ICPB_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
-    if (write_back && n_src > 0 && src_xyz) ICPB_TRY(write_back_source(c, src_xyz, n_src));  // icpengine.cpp:371-375
+    if (write_back && (c->rd_active || (n_src > 0 && src_xyz))) ICPB_TRY(write_back_source(c, src_xyz, n_src));  // icpengine.cpp:371-375
     cudaEvent_t end;
     ICPB_CUDA(c, cudaEventCreate(&end));
     ICPB_CUDA(c, cudaEventRecord(end, c->stream));
@@ -608,7 +599,7 @@ void icp_destroy(icp_handle h) {
     c->workers.clear();
     octree_free(c);
     DevBuf* bufs[] = {&c->tgt_raw, &c->sx, &c->sy, &c->sz, &c->sperm, &c->pos, &c->dist, &c->mask, &c->part_a, &c->part_b,
-                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt, &c->lb, &c->cand, &c->work2};
+                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt, &c->lb, &c->cand, &c->work2, &c->rd_perm, &c->rd_send, &c->rd_recv, &c->rd_tmp, &c->rd_back};
     for (DevBuf* b : bufs) devbuf_free(*b);
     if (c->pin_a.p) cudaFreeHost(c->pin_a.p);
     if (c->pin_b.p) cudaFreeHost(c->pin_b.p);
@@ -698,6 +689,8 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     else if (!strcmp(key, "keep_rcap")) c->opt_keep_rcap = std::min(std::max(value, 0.0), 8.0);
     else if (!strcmp(key, "keep_bias")) c->opt_keep_bias = std::min(std::max((int)value, -4), 4);
     else if (!strcmp(key, "write_mask")) c->opt_write_mask = value != 0.0;
+    else if (!strcmp(key, "redistribute")) c->opt_redistribute = value != 0.0;
+    else if (!strcmp(key, "shard_target")) c->opt_shard_target = value != 0.0;
     else if (!strcmp(key, "lookahead")) c->opt_lookahead = std::min(std::max((int)value, 1), Ctx::REC_RING);
     else {
         c->err = std::string("unknown option ") + key;
@@ -1041,7 +1034,7 @@ int icp_source_upload(icp_handle h, const double* src_xyz, int64_t n_src) {
     ICPB_CUDA(c, cudaSetDevice(c->device));
     ICPB_TRY(upload(c, c->scratch_src, src_xyz, n_src));
     c->src_identity_perm = false;
-    ICPB_TRY(source_from_device_aos(c, (const double*)c->scratch_src.p, n_src));
+    ICPB_TRY(source_from_shard(c, (const double*)c->scratch_src.p, n_src));  // (collective on a sharded handle)
     ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
     return ICP_OK;
 }
@@ -1055,7 +1048,8 @@ int icp_register_resident(icp_handle h, int64_t n_src_global, icp_result* out, d
     ICPB_CUDA(c, cudaSetDevice(c->device));
     bool write_back = true;
     ICPB_TRY(run_loop(c, n_src_global > 0 ? n_src_global : c->n_src, out, stop_flag, &write_back));
-    if (write_back && src_out_xyz && c->n_src > 0) ICPB_TRY(write_back_source(c, src_out_xyz, c->n_src));
+    if (write_back && src_out_xyz && (c->rd_active || c->n_src > 0))
+        ICPB_TRY(write_back_source(c, src_out_xyz, c->rd_active ? c->rd_n_in : c->n_src));
     return out->status;
 }
 

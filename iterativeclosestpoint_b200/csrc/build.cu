@@ -402,6 +402,10 @@ static int radix_sort_pairs(Ctx* c, uint64_t*& keys, uint64_t*& keys_alt, uint32
     return ICP_OK;
 }
 
+int sort_pairs_u64_u32(Ctx* c, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& vals, uint32_t*& vals_alt, int64_t n, int key_bits) {
+    return radix_sort_pairs(c, keys, keys_alt, vals, vals_alt, n, key_bits);
+}
+
 // gather the target into Morton order: (x, y, z, original index)
 __global__ void __launch_bounds__(256) gather_points_kernel(const double* __restrict__ xyz, const uint32_t* __restrict__ idx,
                                                             int64_t n, TPoint* __restrict__ out, uint32_t* __restrict__ pos_of_idx0) {

@@ -78,7 +78,10 @@ struct StatB {
     double sb[3];   // sum (b - pb)
     double sab[9];  // sum (a - pa)(b - pb)^T, row-major
 };
-static constexpr int STATB_DOUBLES = 17;
+// 17 sums + one control word: ranks that were asked to stop put 1 there, so the sum over ranks tells every rank, in the same
+// iteration, that the run is cancelled (ICPEngine::stop(), core/icpengine.cpp:62-66,160-164, on a sharded run)
+static constexpr int STATB_DOUBLES = 18;
+static constexpr int STATB_STOP = 17;
 
 // Per-run device state shared by the iteration kernels (one instance per handle, in device memory).
 struct LoopState {

@@ -6,6 +6,7 @@
 #include <vector>
 #include "common.cuh"
 #include "../../include/icp_b200.h"
+#include <nccl.h>
 
 namespace icpb {
 
@@ -41,7 +42,23 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-struct NcclApi;  // comm.cu
+// ------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time so that the library shares the process's already-loaded libnccl.so.2
+// (torch's bundled copy when driven from Python) and has no link-time dependency for 1-GPU users.
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
 
 struct Ctx {
     int device = 0;
@@ -117,6 +134,7 @@ struct Ctx {
     bool p2p = false;
     bool rs_smem_opt_in = false;  // radix_scatter_kernel's dynamic shared memory opt-in done for this handle's device
     unsigned int mail_epoch = 0;
+    unsigned int mail_run = 0;       // sharded runs started on this handle (the same number on every rank): high part of the epoch
     unsigned long long* d_counters = nullptr;  // see NNArgs::counters (4 entries)
     unsigned int* d_work_count = nullptr;      // mode 4/5: lengths of the two work lists (node_io, work2)
     IterRecord* h_rec = nullptr;  // pinned, device-mapped: ring of REC_RING records, one per iteration enqueued ahead
@@ -136,6 +154,14 @@ struct Ctx {
     void* comm = nullptr;
     int rank = 0, n_ranks = 1;
     DevBuf gather_a, gather_b;
+    // spatial redistribution of the source shards over NVLink (shard.cu): rank r ends up with the r-th slice of the cloud's
+    // spatial order whatever range of the caller's order it was handed; the moved points travel back the same way
+    bool opt_redistribute = true;
+    bool opt_shard_target = true;    // sharded runs: each rank uploads 1/R of the target, an all-gather over NVLink does the rest
+    bool rd_active = false;
+    int64_t rd_n_in = 0, rd_n_recv = 0;
+    int64_t rd_cnt_s[MAIL_RANKS] = {}, rd_cnt_r[MAIL_RANKS] = {};
+    DevBuf rd_perm, rd_send, rd_recv, rd_tmp, rd_back;
 };
 
 #define ICPB_CUDA(ctx, call)                                                                      \
@@ -157,6 +183,22 @@ struct Ctx {
 int devbuf_reserve(Ctx* c, DevBuf& b, size_t bytes);
 int pinned_reserve(Ctx* c, DevBuf& b, size_t bytes);
 void devbuf_free(DevBuf& b);
+
+#define ICPB_NCCL(ctx, call)                                                                   \
+    do {                                                                                       \
+        ncclResult_t r__ = (call);                                                             \
+        if (r__ != ncclSuccess) {                                                              \
+            (ctx)->err = std::string(#call) + ": " + (ctx)->nccl->GetErrorString(r__);         \
+            return ICP_NCCL_ERROR;                                                             \
+        }                                                                                      \
+    } while (0)
+
+// shard.cu: multi-GPU data movement
+NcclApi* nccl_load(Ctx* c);
+int target_upload_sharded(Ctx* c, const double* host_tgt_xyz, int64_t n_tgt);  // 1/R over PCIe per rank, all-gather over NVLink
+int redistribute_source(Ctx* c, const double* d_xyz, int64_t n_in, const double** d_out, int64_t* n_out);
+int redistribute_return(Ctx* c, const double* d_recv_order_xyz, double* d_caller_order_xyz);
+int sort_pairs_u64_u32(Ctx* c, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& vals, uint32_t*& vals_alt, int64_t n, int key_bits);
 
 // build.cu
 int octree_build_device(Ctx* c, const double* d_tgt_xyz, int64_t m, int max_pts, int max_depth);

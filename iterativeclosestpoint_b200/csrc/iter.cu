@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(RED_THREADS, 2) stage_b_kernel(const double* _
                                                               const StatA* __restrict__ rank_a, int n_ranks, int rank, int iter,
                                                               uint8_t* __restrict__ mask_out, double* __restrict__ part,
                                                               double* __restrict__ rank_b, IterRecord* __restrict__ rec,
-                                                              const PeerMail pm) {
+                                                              const PeerMail pm, int stop_req) {
     __shared__ double s_thr;
     __shared__ double s_rb[MAIL_RANKS * STATB_DOUBLES];
     __shared__ double sm_red[RED_THREADS];
@@ -400,6 +400,7 @@ __global__ void __launch_bounds__(RED_THREADS, 2) stage_b_kernel(const double* _
     __threadfence();
     sum_partials_fixed(part, (int)gridDim.x, rank_b + (int64_t)rank * STATB_DOUBLES, sm_red);
     if (threadIdx.x == 0) {
+        rank_b[(int64_t)rank * STATB_DOUBLES + STATB_STOP] = stop_req ? 1.0 : 0.0;
         st->ticket_b = 0u;
         st->a = a_all;
         st->mean = mean;
@@ -489,14 +490,14 @@ int stage_b_blocks(Ctx* c, int64_t n) {
 
 int stage_b_launch(Ctx* c, const double* sx, const double* sy, const double* sz, const uint32_t* pos, const double* dist,
                    int64_t n, int iter, const StatA* rank_a, uint8_t* mask_out, double* part, double* rank_b, const PeerMail* pm,
-                   IterRecord* rec) {
+                   IterRecord* rec, int stop_req) {
     PeerMail none;
     none.epoch = 0u;
     none.n_ranks = 1;
     none.rank = 0;
     const int blocks = stage_b_blocks(c, n);
     stage_b_kernel<<<blocks, RED_THREADS, 0, c->stream>>>(sx, sy, sz, pos, dist, n, c->fast.pts, c->d_state, rank_a, c->n_ranks,
-                                                          c->rank, iter, mask_out, part, rank_b, rec ? rec : c->d_rec, pm ? *pm : none);
+                                                          c->rank, iter, mask_out, part, rank_b, rec ? rec : c->d_rec, pm ? *pm : none, stop_req);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
     return ICP_OK;

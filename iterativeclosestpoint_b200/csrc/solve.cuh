@@ -225,6 +225,16 @@ static __device__ __noinline__ void solve_step(LoopState* st, const double* rank
         for (int r = 1; r < n_ranks; ++r) v += rank_parts[(int64_t)r * STATB_DOUBLES + k];
         b[k] = v;
     }
+    if (b[STATB_STOP] > 0.0) {
+        // some rank was asked to stop: every rank leaves here, in the same iteration, with nothing of this iteration recorded
+        // (the reference polls its flag before the iteration's work, core/icpengine.cpp:160-164)
+        st->exit_code = 4;
+        st->have_T = 0;
+        rec->iteration = st->iter + 1;
+        rec->exit_code = 4;
+        __threadfence_system();
+        return;
+    }
     const double valid = b[0];
     const double rmse = valid > 0.0 ? dsqrt(ddiv(b[1], valid)) : 0.0;  // icpengine.cpp:274
     st->rmse = rmse;

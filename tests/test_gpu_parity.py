@@ -322,6 +322,29 @@ def test_register_divergence_and_max_iterations(handle, oracle):
         assert np.max(np.abs(work - want.source_out)) <= 1e-9 * float(np.max(np.abs(want.source_out)))
 
 
+def test_full_size_config2_whole_runs_against_the_oracle(handle, oracle):
+    """BASELINE.json config #2 at full size (1M <-> 1M) as WHOLE RUNS against the oracle (its NN loop on all host threads):
+    the 5 deg / 0.5 m pose the config names for its first iterations, and a complete registration to the reference's own
+    convergence rule from the primary pose.  Identical iteration counts and inlier counts, transforms within 1e-9."""
+    nthr = oracle.hw_threads()
+    src, tgt = synth.make_pair(1_000_000, 2, "stress")
+    want = oracle.icp(src, tgt, max_iterations=4, nthreads=nthr)
+    handle.set_params(ICPParameters(maxIterations=4))
+    work = src.copy()
+    got = handle.register(work, tgt)
+    _check_run(got, want, len(src))
+    assert np.max(np.abs(work - want.source_out)) <= 1e-9 * float(np.max(np.abs(want.source_out)))
+    src, _ = synth.make_pair(1_000_000, 2, "primary")
+    want = oracle.icp(src, tgt, nthreads=nthr)
+    handle.set_params(ICPParameters())
+    work = src.copy()
+    got = handle.register(work, tgt)
+    assert want.total_iterations > 8, "the fixture should be a real multi-iteration registration"
+    _check_run(got, want, len(src))
+    assert [h.validPoints for h in got.iterationHistory] == [h.valid_points for h in want.history]
+    assert np.max(np.abs(work - want.source_out)) <= 1e-9 * float(np.max(np.abs(want.source_out)))
+
+
 def test_full_size_config2_properties(handle, oracle):
     """BASELINE.json config #2 at full size (1M <-> 1M): index parity on a 50k sample against the oracle, plus
     size-independent properties on all queries (idempotence, self-match, brute-force distance on a subsample)."""
@@ -445,7 +468,20 @@ def test_full_size_config3_sample_parity_and_properties(handle, oracle):
     idx2, _, _ = handle.nn_query(moved)
     sample = r[80000:120000]
     assert np.array_equal(idx2[sample], otree.find_nearest(moved[sample], nthreads=oracle.hw_threads()))
-    # inlier counts of the three iterations against the oracle's statistics on the GPU's own correspondences
+    # the statistics of an iteration over ALL 10M points against the oracle's, on the same correspondences, at both poses:
+    # inlier mask bit-exact, threshold / mean / std / RMSE to 1e-12, inlier count identical -- and the registration's own
+    # first record must be that iteration
+    for pose, ii, k in ((src, idx, 0), (moved, idx2, 3)):
+        od, omask, ost = oracle.iteration_stats(pose, tgt, ii, k)
+        gd, gmask, gst = handle.iteration_stats(pose, ii, k)
+        assert np.array_equal(gmask, omask), f"iteration {k}: inlier masks differ"
+        assert np.array_equal(gd, od), f"iteration {k}: distances differ"
+        assert gst.valid_count == ost.valid_count and gst.outlier_count == ost.outlier_count
+        for name in ("mean", "std_dev", "threshold", "rmse"):
+            assert abs(getattr(gst, name) - getattr(ost, name)) <= REL_SUM * abs(getattr(ost, name)), (k, name)
+        if k == 0:
+            first = res.iterationHistory[0]
+            assert first.validPoints == ost.valid_count and abs(first.rmse - ost.rmse) <= REL_SUM * ost.rmse
     assert all(h.validPoints + h.outlierPoints == len(src) for h in res.iterationHistory)
     # the whole registration to convergence at full size: the default mode (balanced walk, then keep / collect with bounds
     # carried between iterations) must reproduce the one-thread-per-query walk bit for bit -- every index and distance of

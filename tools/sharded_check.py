@@ -40,9 +40,32 @@ t = torch.tensor(res.cumulativeT.reshape(-1), dtype=torch.float64, device="cuda"
 g = [torch.empty_like(t) for _ in range(world)]
 dist.all_gather(g, t)
 check(all(torch.equal(g[0], x) for x in g), "ranks disagree on the cumulative transform bits")
+# the resident entry points take the same road (redistribution over NVLink, return on write-back)
+h.source_upload(np.ascontiguousarray(src[lo:hi]))
+back = np.zeros((hi - lo, 3))
+res2 = h.register_resident(m, source_out=back)
+check(res2.totalIterations == ref.totalIterations and np.array_equal(res2.cumulativeT, res.cumulativeT), "resident run differs from icp_register_sharded")
+check(np.array_equal(back, shard), "resident write-back differs")
+# a stop request on ONE rank must end the run on EVERY rank in the same iteration, sources untouched (icpengine.cpp:160-164)
+import ctypes
+stop = ctypes.c_int(1 if rank == world - 1 else 0)
+shard3 = np.ascontiguousarray(src[lo:hi]).copy()
+res3 = h.register_sharded(shard3, m, tgt, stop_flag=stop)
+check(res3.status == 2 and not res3.success and res3.totalIterations == 0, f"stop: status {res3.status} iterations {res3.totalIterations}")
+check(np.array_equal(shard3, src[lo:hi]), "stop: the source was touched")
+# ... and the next run on the same handles is unharmed (epochs keyed on the run)
+shard4 = np.ascontiguousarray(src[lo:hi]).copy()
+res4 = h.register_sharded(shard4, m, tgt)
+check(np.array_equal(res4.cumulativeT, res.cumulativeT) and np.array_equal(shard4, shard), "run after a cancelled run differs")
 flag = torch.tensor([1 if ok else 0], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(json.dumps({"sharded_parity_ok": bool(flag.item()), "world": world, "points": m, "iterations": res.totalIterations,
-                      "final_rmse": res.finalRMSE, "notes": notes[:5]}), flush=True)
+    line = {"sharded_parity_ok": bool(flag.item()), "world": world, "points": m, "iterations": res.totalIterations,
+            "final_rmse": res.finalRMSE, "checks": ["iterations / inlier counts equal the 1-GPU run", "transforms <= 1e-12, rmse <= 1e-10 vs 1-GPU",
+            "moved shards <= 1e-12 vs 1-GPU", "ranks bit-identical", "resident path == host path", "stop on one rank cancels all ranks",
+            "run after a cancelled run unharmed"], "timings_ms": {k: round(float(v), 3) for k, v in res.timings_ms.items()}, "notes": notes[:5]}
+    print(json.dumps(line), flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/sharded_check_{world}gpu_{m}.json", "w") as f:
+        json.dump(line, f)
 dist.barrier(); dist.destroy_process_group(); h.close(); h1.close()
 sys.exit(0 if flag.item() else 1)
