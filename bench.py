@@ -105,11 +105,13 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------------
-def make_workload(m: int, regime: str):
-    from iterativeclosestpoint_b200 import synth
+def make_workload(m: int, regime: str, local_rank: int = 0, world: int = 1, barrier=None):
+    """The seeded synthetic pair; with several ranks on the node it is generated once and shared (sharding.shared_pair)."""
+    from iterativeclosestpoint_b200 import sharding
     t0 = time.time()
-    src, tgt = synth.make_pair(m, 3, regime)
-    log(f"[bench] generated {m} <-> {m} points ({regime}) in {time.time() - t0:.1f}s")
+    src, tgt = sharding.shared_pair(m, 3, regime, local_rank, world, barrier)
+    if local_rank == 0:
+        log(f"[bench] generated {m} <-> {m} points ({regime}) in {time.time() - t0:.1f}s")
     return src, tgt
 
 
@@ -439,7 +441,7 @@ def main():
 
     from iterativeclosestpoint_b200 import sharding
 
-    src, tgt = make_workload(M, args.regime)
+    src, tgt = make_workload(M, args.regime, local_rank, world, (lambda: dist.barrier()) if world > 1 else None)
     shard_idx = None
     if args.shard == "spatial" and world > 1:
         shard_idx = sharding.shard_spatial(src, rank, world)  # host-side preparation (NOT what a drop-in caller gets for free)
@@ -467,7 +469,11 @@ def main():
     # back (apply fused into the load) + 4 B match + 8 B distance per query, the 24 B/point target once, the node table once
     alg_bytes = 60 * n_local + 24 * M + int(info.node_bytes)
 
-    # (1) one whole registration under the reference defaults: warm-up (>= W iterations), phases, parity
+    # (1) one whole registration under the reference defaults: warm-up (>= W iterations), phases, parity.  Two throw-away
+    # iterations first, so that the handle's buffers exist before anything is looked at (cudaMalloc inside the first run).
+    h.set_params(ICPParameters(maxIterations=2))
+    h.register_resident(M)
+    upload(shard)
     h.set_params(ICPParameters())
     barrier()
     full = h.register_resident(M)
@@ -526,6 +532,10 @@ def main():
     if not args.no_e2e:
         pin_s, host_src = pinned_copy(shard)
         pin_t, host_tgt = pinned_copy(tgt)
+        h.set_params(ICPParameters(maxIterations=2))
+        work0 = host_src.copy()
+        (h.register_sharded(work0, M, host_tgt) if world > 1 else h.register(work0, host_tgt))  # untimed: first use of the path
+        del work0                                                        # (buffers, NCCL point-to-point channels)
         h.set_params(ICPParameters())
         barrier()
         t0 = time.perf_counter()

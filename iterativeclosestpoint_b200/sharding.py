@@ -78,6 +78,33 @@ def shard_spatial(points: np.ndarray, rank: int, world: int, order: np.ndarray |
     return np.sort(order[lo:hi])
 
 
+def shared_pair(m: int, config: int, regime: str, local_rank: int, world: int, barrier, tag: str = ""):
+    """The seeded synthetic pair (synth.make_pair) for several ranks of one node: local rank 0 generates it once, the others
+    map the same pages read-only (a 10^8-point pair is 4.8 GB; eight private copies plus the generator's temporaries are not
+    needed).  `barrier` is a callable that synchronises the node's ranks."""
+    import os
+    from . import synth
+    if world <= 1 or barrier is None:
+        return synth.make_pair(m, config, regime)
+    base = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"icpb_pair_{m}_{config}_{regime}_{os.environ.get('MASTER_PORT', '0')}{tag}")
+    if local_rank == 0:
+        src, tgt = synth.make_pair(m, config, regime)
+        np.save(base + "_src.npy", src)
+        np.save(base + "_tgt.npy", tgt)
+    barrier()
+    if local_rank != 0:
+        src = np.load(base + "_src.npy", mmap_mode="r")
+        tgt = np.load(base + "_tgt.npy", mmap_mode="r")
+    barrier()
+    if local_rank == 0:
+        for suffix in ("_src.npy", "_tgt.npy"):  # (the mappings keep the pages alive)
+            try:
+                os.unlink(base + suffix)
+            except OSError:
+                pass
+    return src, tgt
+
+
 def exchange_unique_id(handle, dist, rank: int, src: int = 0) -> bytes:
     """Rank `src` creates the NCCL unique id through the C ABI (icp_comm_unique_id); everyone receives it."""
     box = [handle.comm_unique_id() if rank == src else None]
