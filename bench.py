@@ -313,9 +313,12 @@ def batch_main(args):
             line["cpu_baseline"] = {"value": PTS * rits / dt, "unit": UNIT, "cores": threads, "kind": kind, "pairs_per_s": nsub / dt,
                                     "sample": f"{nsub} of {NP} pairs, whole registrations, one pair per host thread at a time"}
             bad_it = sum(1 for a, b in zip(res[:nsub], ref) if int(a.totalIterations) != int(b.total_iterations))
-            t_rel = max(float(np.max(np.abs(np.asarray(a.cumulativeT) - np.asarray(b.cum_T))) / max(1e-300, float(np.max(np.abs(b.cum_T)))))
-                        for a, b in zip(res[:nsub], ref))
-            line["parity"] = {"pairs_checked": nsub, "iteration_count_mismatches": bad_it, "T_cum_max_rel": t_rel, "checker": kind}
+            def dev(a, b):
+                return max(float(np.max(np.abs(np.asarray(a.finalR) - np.asarray(b.final_R)))),
+                           float(np.max(np.abs(np.asarray(a.finalT) - np.asarray(b.final_t))) / max(1.0, float(np.max(np.abs(b.final_t))))))
+            t_rel = max(dev(a, b) for a, b in zip(res[:nsub], ref))
+            line["parity"] = {"pairs_checked": nsub, "iteration_count_mismatches": bad_it, "final_R_t_max_dev": t_rel,
+                              "within_1e-9": bool(t_rel <= 1e-9 and bad_it == 0), "checker": kind}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

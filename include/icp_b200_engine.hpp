@@ -99,7 +99,10 @@ public:
 
     void setParameters(const ICPParameters& p) { params_ = p; }  // icpengine.cpp:19-22
     ICPParameters getParameters() const { return params_; }
-    void stop() { stop_.store(1); }                              // icpengine.cpp:62-66 (atomic here)
+    void stop() {                                                // icpengine.cpp:62-66 (atomic here)
+        stop_.store(1);
+        if (logMessage) logMessage(u8"用户请求停止配准...");
+    }
     ICPResult getResult() const { return result_; }
     icp_handle handle() const { return h_; }
 

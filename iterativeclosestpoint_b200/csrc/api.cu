@@ -141,16 +141,23 @@ struct RunAcc {
     bool consume(const IterRecord& rec, int iter, float nn_ms, float iter_ms, bool notify) {
         out->loop_iterations = iter + 1;
         if (rec.exit_code == 4) {  // a rank of a sharded run was asked to stop (icpengine.cpp:160-164): nothing of this iteration counts
-            log_msg(c, "registration stopped");
+            log_msg(c, u8"配准已停止");
             out->status = ICP_CANCELLED;
             out->loop_iterations = iter;
             write_back = false;
             return false;
         }
-        if (rec.problems > 0.0) log_msg(c, "warning: %.0f abnormal distance values", rec.problems);
-        log_msg(c, "  distance range: min=%.6f, max=%.6f", rec.dmin, rec.dmax);
-        log_msg(c, "  distance stats: mean=%.6f, std=%.6f, threshold=%.6f", rec.mean, rec.std_dev, rec.threshold);
-        log_msg(c, "  RMSE = %.6f (valid: %d/%lld, outliers removed: %d)", rec.rmse, rec.valid_points, n_global, rec.outlier_points);
+        // the reference's own texts (core/icpengine.cpp:227-232,257-260,280-284; CLI: one console line per iteration,
+        // icp_registration.cpp:478,543-545)
+        if (variant == ICP_VARIANT_ENGINE) {
+            if (rec.problems > 0.0) log_msg(c, u8"警告: 发现 %.0f 个异常距离值", rec.problems);
+            log_msg(c, u8"  距离范围: 最小=%.6f, 最大=%.6f", rec.dmin, rec.dmax);
+            log_msg(c, u8"  距离统计: 均值=%.6f, 标准差=%.6f, 阈值=%.6f", rec.mean, rec.std_dev, rec.threshold);
+            log_msg(c, u8"  RMSE = %.6f (有效点: %d/%lld, 剔除离群点: %d)", rec.rmse, rec.valid_points, n_global, rec.outlier_points);
+        } else {
+            log_msg(c, u8"迭代 %d/%d ... RMSE = %g (有效点: %d/%lld, 剔除离群点: %d)", iter + 1, max_iterations, rec.rmse, rec.valid_points,
+                    n_global, rec.outlier_points);
+        }
         std::memcpy(T_cum, rec.T_cum, sizeof T_cum);
         std::memcpy(T_last, rec.T_last, sizeof T_last);
         if (rec.exit_code == 0 || rec.exit_code == 3) prev_error = rec.rmse;
@@ -164,7 +171,7 @@ struct RunAcc {
         it.iter_ms = iter_ms;
         std::memcpy(it.transform, rec.T_cum, sizeof it.transform);
         if (rec.exit_code == 1) {  // converged: icpengine.cpp:291-305 ; CLI :551-554
-            log_msg(c, "converged at iteration %d", iter + 1);
+            log_msg(c, u8"收敛达到! 迭代次数: %d", iter + 1);  // icpengine.cpp:291 ; icp_registration.cpp:552
             if (variant == ICP_VARIANT_ENGINE) {
                 it.has_angles = 0;  // the reference leaves the angle fields of this record unset (:294-303)
                 push(it, notify);
@@ -172,11 +179,12 @@ struct RunAcc {
             return false;
         }
         if (rec.exit_code == 2) {  // error grew: icpengine.cpp:311-314
-            log_msg(c, "warning: error increased, stopping");
+            log_msg(c, variant == ICP_VARIANT_ENGINE ? u8"警告: 误差增加，停止迭代" : u8"警告: 误差增加,停止迭代。");  // :312 ; CLI :560
             return false;
         }
         if (rec.exit_code == 3) {  // < 3 inliers: icpengine.cpp:319-323 ; CLI :567-570 breaks and writes back
-            log_msg(c, "error: too few valid pairs to estimate a transform");
+            log_msg(c, variant == ICP_VARIANT_ENGINE ? u8"错误: 有效点对不足，无法计算变换"
+                                                     : u8"警告: 有效点对太少（< 3），无法计算变换，停止迭代。");  // :320 ; CLI :568
             if (variant == ICP_VARIANT_ENGINE) {
                 out->status = ICP_TOO_FEW_INLIERS;
                 write_back = false;
@@ -246,8 +254,6 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
 
     const bool resume = c->prev_valid;  // same resident source and tree as the last run: its matches seed this one
     c->prev_valid = false;
-    if (c->opt_nn_mode == 2 && !resume)  // per-tile start nodes: the root until a tile has searched once
-        ICPB_CUDA(c, cudaMemsetAsync(c->node_io.p, 0, (size_t)((n + 31) / 32) * sizeof(uint32_t), c->stream));
     if (c->opt_nn_mode == 4)  // temporal bounds belong to one run: the source moves between runs
         ICPB_CUDA(c, cudaMemsetAsync(c->lb.p, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(float), c->stream));
     // modes 5 / 6: candidates and bounds survive between runs over the same resident source and tree (the loop's last
@@ -271,7 +277,7 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
     // every record as it is produced (the reference calls back and polls stop() once per iteration, icpengine.cpp:160-164,364-367).
     const bool debug_iter = c->opt_count && getenv("ICP_B200_DEBUG_ITER");
     const bool each = stop_flag || c->on_iteration || c->on_progress || c->on_log || debug_iter ||
-                      !(c->opt_nn_mode == 0 || c->opt_nn_mode == 1 || c->opt_nn_mode == 3);
+                      !(c->opt_nn_mode == 0 || c->opt_nn_mode == 3);
     const int ahead = each ? 1 : std::min(std::max(c->opt_lookahead, 1), (int)Ctx::REC_RING);
     bool go_on = true;
     for (int iter0 = 0; iter0 < P.max_iterations && go_on; iter0 += ahead) {
@@ -282,13 +288,13 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         // (solve_step, exit code 4) -- a rank that broke out here would leave its peers waiting for its records.
         const int stop_req = (variant == ICP_VARIANT_ENGINE && stop_flag && *stop_flag) ? 1 : 0;
         if (stop_req && c->n_ranks <= 1) {  // icpengine.cpp:160-164
-            log_msg(c, "registration stopped");
+            log_msg(c, u8"配准已停止");
             out->status = ICP_CANCELLED;
             acc.write_back = false;
             go_on = false;
             break;
         }
-        log_msg(c, "iteration %d/%d ...", iter + 1, P.max_iterations);
+        if (variant == ICP_VARIANT_ENGINE) log_msg(c, u8"迭代 %d/%d ...", iter + 1, P.max_iterations);  // icpengine.cpp:166
         c->h_rec[slot].iteration = 0;  // (an iteration that found the loop ended leaves its record untouched)
 
         NNLaunch L;
@@ -298,8 +304,7 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         L.pos_out = (uint32_t*)c->pos.p;
         L.dist_out = (double*)c->dist.p;
         L.prev_pos = ((iter > 0 || resume) && c->opt_nn_mode >= 1) ? (uint32_t*)c->pos.p : nullptr;
-        L.node_io = (c->opt_nn_mode == 1) ? (uint32_t*)c->node_io.p : nullptr;
-        L.tile_node = (c->opt_nn_mode == 2) ? (uint32_t*)c->node_io.p : nullptr;
+        L.node_io = nullptr;
         L.lb_io = (float*)c->lb.p;
         L.cand_io = (c->opt_nn_mode >= 5) ? (uint4*)c->cand.p : nullptr;
         L.part_a = nullptr;
@@ -464,6 +469,39 @@ static int stage_cloud(Ctx* c, cudaStream_t st, DevBuf& dst, DevBuf& rec_stage, 
     return las_decode_launch(c, st, (const uint8_t*)rec_stage.p, n, las->record_length, las->scale, las->offset, (double*)dst.p);
 }
 
+// "八叉树测试" (core/icpengine.cpp:127-137): the reference looks up the nearest target point of the FIRST source point before the
+// loop and logs it.  One query through the literal traversal, only when a log callback is installed.
+static int log_octree_test(Ctx* c, const double* src_xyz, const double* tgt_xyz) {
+    ICPB_TRY(devbuf_reserve(c, c->scratch3, 256));
+    double* d = (double*)c->scratch3.p;  // x, y, z, dist, pos
+    ICPB_CUDA(c, cudaMemcpyAsync(d, src_xyz, 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NNLaunch L;
+    L.sx = d; L.sy = d + 1; L.sz = d + 2;
+    L.ox = L.oy = L.oz = nullptr;
+    L.n = 1;
+    L.pos_out = (uint32_t*)(d + 4);
+    L.dist_out = d + 3;
+    L.prev_pos = nullptr;
+    L.node_io = nullptr;
+    L.part_a = nullptr;
+    L.state = nullptr;
+    L.apply_pending = 0;
+    L.mode = 0;
+    L.init_best = DBL_MAX;
+    ICPB_TRY(nn_launch(c, L));
+    double dist = 0.0;
+    uint32_t pos = 0;
+    ICPB_CUDA(c, cudaMemcpyAsync(&dist, d + 3, sizeof dist, cudaMemcpyDeviceToHost, c->stream));
+    ICPB_CUDA(c, cudaMemcpyAsync(&pos, d + 4, sizeof pos, cudaMemcpyDeviceToHost, c->stream));
+    ICPB_CUDA(c, cudaStreamSynchronize(c->stream));
+    TPoint tp;
+    ICPB_CUDA(c, cudaMemcpy(&tp, c->fast.pts + pos, sizeof tp, cudaMemcpyDeviceToHost));
+    const long long idx = tp.idx;
+    log_msg(c, u8"八叉树测试: 查询点(%.3f,%.3f,%.3f) -> 最近点[%lld](%.3f,%.3f,%.3f), 距离=%.3f", src_xyz[0], src_xyz[1], src_xyz[2], idx,
+            tgt_xyz[3 * idx], tgt_xyz[3 * idx + 1], tgt_xyz[3 * idx + 2], dist);
+    return ICP_OK;
+}
+
 static int register_impl(Ctx* c, double* src_xyz, int64_t n_src, int64_t n_src_global, const double* tgt_xyz, int64_t n_tgt,
                          icp_result* out, const volatile int* stop_flag, const icp_las_points* src_las = nullptr,
                          const icp_las_points* tgt_las = nullptr) {
@@ -476,9 +514,14 @@ static int register_impl(Ctx* c, double* src_xyz, int64_t n_src, int64_t n_src_g
     const icp_params& P = c->params;
     const int leaf = (P.variant == ICP_VARIANT_CLI) ? 10 : P.octree_max_points;  // icp_registration.cpp:454
     const int depth = (P.variant == ICP_VARIANT_CLI) ? 20 : P.octree_max_depth;
-    log_msg(c, "========== ICP registration start ==========");
-    log_msg(c, "source: %lld points", (long long)n_src_global);
-    log_msg(c, "target: %lld points", (long long)n_tgt);
+    const bool engine_log = P.variant == ICP_VARIANT_ENGINE;
+    log_msg(c, engine_log ? u8"========== 开始ICP配准 ==========" : u8"开始ICP精匹配...");  // icpengine.cpp:43-45 ; CLI :448-450
+    log_msg(c, u8"源点云: %lld 个点", (long long)n_src_global);
+    log_msg(c, u8"目标点云: %lld 个点", (long long)n_tgt);
+    if (engine_log && c->n_ranks <= 1) {  // icpengine.cpp:48-57
+        if (src_xyz && n_src > 0) log_msg(c, u8"源点云第一个点: (%.3f, %.3f, %.3f)", src_xyz[0], src_xyz[1], src_xyz[2]);
+        if (tgt_xyz && n_tgt > 0) log_msg(c, u8"目标点云第一个点: (%.3f, %.3f, %.3f)", tgt_xyz[0], tgt_xyz[1], tgt_xyz[2]);
+    }
 
     ICPB_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
     if (c->n_ranks > 1 && c->comm && c->opt_shard_target && tgt_xyz && !tgt_las)
@@ -496,10 +539,10 @@ static int register_impl(Ctx* c, double* src_xyz, int64_t n_src, int64_t n_src_g
         ICPB_TRY(stage_cloud(c, c->stream2, src_stage, c->las_src, src_xyz, src_las, n_src));
         ICPB_CUDA(c, cudaEventRecord(c->ev_src, c->stream2));
     }
-    log_msg(c, "building the target octree ...");
+    if (engine_log) log_msg(c, u8"构建目标点云八叉树索引...");  // icpengine.cpp:119
     ICPB_TRY(octree_build_device(c, (const double*)c->tgt_raw.p, n_tgt, leaf, depth));
-    log_msg(c, "octree built: %lld nodes, %lld leaves, depth %d", (long long)c->tree.n_nodes, (long long)c->tree.n_leaves,
-            c->tree.depth);
+    log_msg(c, engine_log ? u8"八叉树构建完成!" : u8"构建八叉树索引... 完成!");  // :124 ; CLI :453-455
+    if (engine_log && c->on_log && c->n_ranks <= 1 && src_xyz && tgt_xyz && n_src > 0) ICPB_TRY(log_octree_test(c, src_xyz, tgt_xyz));
     c->src_identity_perm = false;
     c->n_src = n_src;
     if (n_src > 0) ICPB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_src, 0));
@@ -519,9 +562,13 @@ static int register_impl(Ctx* c, double* src_xyz, int64_t n_src, int64_t n_src_g
     cudaEventElapsedTime(&out->ms_d2h, c->ev[7], end);
     cudaEventDestroy(end);
     if (out->status == ICP_OK) {
-        log_msg(c, "========== registration finished ==========");
-        log_msg(c, "total iterations: %d", out->total_iterations);
-        log_msg(c, "final RMSE: %.6f", out->final_rmse);
+        if (engine_log) {  // icpengine.cpp:389-391
+            log_msg(c, u8"========== 配准完成 ==========");
+            log_msg(c, u8"总迭代次数: %d", out->total_iterations);
+            log_msg(c, u8"最终RMSE: %.6f", out->final_rmse);
+        } else {
+            log_msg(c, u8"最终RMSE: %g", out->final_rmse);  // icp_registration.cpp:606
+        }
     }
     return out->status;
 }
@@ -584,7 +631,7 @@ int icp_create(icp_handle* out, int device_id) {
     if (cudaHostGetDevicePointer(&c->d_rec, c->h_rec, 0) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (getenv("ICP_B200_DEBUG_COUNTERS")) c->opt_count = true;
     const char* m = getenv("ICP_B200_NN_MODE");
-    if (m) c->opt_nn_mode = std::min(std::max(atoi(m), 0), 6);
+    if (m && (atoi(m) == 0 || (atoi(m) >= 3 && atoi(m) <= 6))) c->opt_nn_mode = atoi(m);
     *out = (icp_handle)c;
     return ICP_OK;
 }
@@ -599,7 +646,7 @@ void icp_destroy(icp_handle h) {
     c->workers.clear();
     octree_free(c);
     DevBuf* bufs[] = {&c->tgt_raw, &c->sx, &c->sy, &c->sz, &c->sperm, &c->pos, &c->dist, &c->mask, &c->part_a, &c->part_b,
-                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt, &c->lb, &c->cand, &c->work2, &c->rd_perm, &c->rd_send, &c->rd_recv, &c->rd_tmp, &c->rd_back};
+                      &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3, &c->scratch_src, &c->gather_a, &c->gather_b, &c->node_io, &c->las_src, &c->las_tgt, &c->lb, &c->cand, &c->work2, &c->rd_perm, &c->rd_send, &c->rd_recv, &c->rd_tmp, &c->rd_back, &c->scratch_keys};
     for (DevBuf* b : bufs) devbuf_free(*b);
     if (c->pin_a.p) cudaFreeHost(c->pin_a.p);
     if (c->pin_b.p) cudaFreeHost(c->pin_b.p);
@@ -633,8 +680,8 @@ int icp_set_params(icp_handle h, const icp_params* p) {
         c->err = "params: unknown variant";
         return ICP_INVALID_ARGUMENT;
     }
-    if (p->octree_max_depth < 0 || p->octree_max_depth > 21) {
-        c->err = "params: octree_max_depth must be in [0,21] (3 bits per level in a 64-bit key)";
+    if (p->octree_max_depth < 0 || p->octree_max_depth > 63) {  // (the reference's GUI offers 10 .. 50, settingspage.cpp:76)
+        c->err = "params: octree_max_depth must be in [0,63]";
         return ICP_INVALID_ARGUMENT;
     }
     c->params = *p;
@@ -662,7 +709,12 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     Ctx* c = (Ctx*)h;
     if (!c || !key) return ICP_INVALID_ARGUMENT;
     if (!strcmp(key, "nn_mode")) {
-        c->opt_nn_mode = std::min(std::max((int)(value + 0.5), 0), 6);
+        const int m = (int)(value + 0.5);
+        if (!(m == 0 || (m >= 3 && m <= 6))) {
+            c->err = "nn_mode: 0 literal traversal, 3 per-thread cell walk, 4 balanced walk, 5 keep / collect, 6 automatic (default)";
+            return ICP_INVALID_ARGUMENT;
+        }
+        c->opt_nn_mode = m;
         c->prev_valid = false;
     }
     else if (!strcmp(key, "count")) c->opt_count = value != 0.0;
@@ -677,7 +729,6 @@ int icp_set_option(icp_handle h, const char* key, double value) {
     else if (!strcmp(key, "grid_shift")) c->opt_grid_shift = (int)value;
     else if (!strcmp(key, "grid_max_cells")) c->opt_grid_max_cells = std::max((long long)value, 1ll);
     else if (!strcmp(key, "walk_max_cells")) c->opt_walk_max_cells = std::max((int)value, 1);
-    else if (!strcmp(key, "terminal_pts")) c->opt_terminal_pts = std::min(std::max((int)value, 1), 1024);
     else if (!strcmp(key, "search_leaf")) c->opt_search_leaf = std::min(std::max((int)value, 1), 1024);
     else if (!strcmp(key, "order_queries")) c->opt_order_queries = value != 0.0;
     else if (!strcmp(key, "nn_chunks")) c->opt_nn_chunks = std::min(std::max((int)value, 1), 8);

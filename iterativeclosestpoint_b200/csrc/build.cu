@@ -219,6 +219,10 @@ __global__ void cube_root_kernel(double* __restrict__ root) {
 // ------------------------------------------------------------------------------------------------
 // K1: octant-path keys by FP64 bisection (octree.cpp:97-110 applied max_depth times)
 // ------------------------------------------------------------------------------------------------
+// A 64-bit word holds 21 levels; a deeper tree (the reference accepts octreeMaxDepth up to 50, settingspage.cpp:76) takes
+// ceil(max_depth / 21) words per point: word w of point i at keys[w * n + i], most significant word first.
+constexpr int KEY_LEVELS = 21;
+
 __global__ void __launch_bounds__(256) morton_keys_kernel(const double* __restrict__ xyz, int64_t n,
                                                           const double* __restrict__ root, int max_depth,
                                                           uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
@@ -232,6 +236,7 @@ __global__ void __launch_bounds__(256) morton_keys_kernel(const double* __restri
         p[a] = xyz[3 * i + a];
     }
     uint64_t key = 0;
+    int word = 0;
     for (int d = 0; d < max_depth; ++d) {
         uint32_t oct = 0;
 #pragma unroll
@@ -243,8 +248,13 @@ __global__ void __launch_bounds__(256) morton_keys_kernel(const double* __restri
             hi[a] = up ? hi[a] : mid;
         }
         key = (key << 3) | oct;
+        if ((d + 1) % KEY_LEVELS == 0 && d + 1 < max_depth) {
+            keys[(int64_t)word * n + i] = key;
+            key = 0;
+            ++word;
+        }
     }
-    keys[i] = key;
+    keys[(int64_t)word * n + i] = key;
     idx[i] = (uint32_t)i;
 }
 
@@ -406,6 +416,12 @@ int sort_pairs_u64_u32(Ctx* c, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& 
     return radix_sort_pairs(c, keys, keys_alt, vals, vals_alt, n, key_bits);
 }
 
+__global__ void __launch_bounds__(256) gather_u64_kernel(const uint64_t* __restrict__ in, const uint32_t* __restrict__ idx, int64_t n,
+                                                         uint64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[idx[i]];
+}
+
 // gather the target into Morton order: (x, y, z, original index)
 __global__ void __launch_bounds__(256) gather_points_kernel(const double* __restrict__ xyz, const uint32_t* __restrict__ idx,
                                                             int64_t n, TPoint* __restrict__ out, uint32_t* __restrict__ pos_of_idx0) {
@@ -439,13 +455,12 @@ __device__ __forceinline__ uint32_t lower_bound_octant(const uint64_t* __restric
 // counts[i] = number of non-empty octants of level node i (0 for leaves)
 __global__ void __launch_bounds__(128) node_count_kernel(const Node* __restrict__ nodes, uint32_t first, uint32_t count,
                                                          const uint64_t* __restrict__ keys, int level, int max_pts,
-                                                         int max_depth, uint32_t* __restrict__ counts) {
+                                                         int max_depth, int shift, uint32_t* __restrict__ counts) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     const Node& nd = nodes[first + t];
     uint32_t nchild = 0;
     if (!(nd.npts <= (uint32_t)max_pts || level >= max_depth)) {  // octree.cpp:88
-        const int shift = 3 * (max_depth - 1 - level);
         uint32_t b = nd.pt0;
         const uint32_t end = nd.pt0 + nd.npts;
         for (uint32_t oct = 1; oct <= 8; ++oct) {
@@ -459,7 +474,7 @@ __global__ void __launch_bounds__(128) node_count_kernel(const Node* __restrict_
 
 __global__ void __launch_bounds__(128) node_emit_kernel(Node* __restrict__ nodes, uint32_t first, uint32_t count,
                                                         const uint64_t* __restrict__ keys, int level, int max_pts,
-                                                        int max_depth, const uint32_t* __restrict__ child_off,
+                                                        int max_depth, int shift, const uint32_t* __restrict__ child_off,
                                                         uint32_t next_first, uint32_t* __restrict__ leaf_counter,
                                                         uint32_t* __restrict__ parent, uint64_t* __restrict__ cell) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -471,7 +486,6 @@ __global__ void __launch_bounds__(128) node_emit_kernel(Node* __restrict__ nodes
         atomicAdd(leaf_counter, 1u);
         return;
     }
-    const int shift = 3 * (max_depth - 1 - level);
     double mid[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) mid[a] = dmul(dadd(nd.lo[a], nd.hi[a]), 0.5);  // octree.cpp:97-99
@@ -615,12 +629,32 @@ static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, i
     idx = (uint32_t*)(keys_alt + m);
     idx_alt = idx + m;
     const int kb = (int)((m + 255) / 256);
-    morton_keys_kernel<<<kb, 256, 0, s>>>(d_xyz, m, d_root, max_depth, keys, idx);
-    c->launches++;
-
-    // K2
-    const int key_bits = 3 * max_depth;
-    if (key_bits > 0) ICPB_TRY(radix_sort_pairs(c, keys, keys_alt, idx, idx_alt, m, key_bits));
+    const int n_words = std::max(1, (max_depth + KEY_LEVELS - 1) / KEY_LEVELS);
+    auto word_levels = [&](int w) { return std::min(KEY_LEVELS, max_depth - KEY_LEVELS * w); };
+    uint64_t* words_sorted = nullptr;  // deep trees: [n_words][m], sorted order
+    if (n_words == 1) {
+        morton_keys_kernel<<<kb, 256, 0, s>>>(d_xyz, m, d_root, max_depth, keys, idx);
+        c->launches++;
+        // K2
+        const int key_bits = 3 * max_depth;
+        if (key_bits > 0) ICPB_TRY(radix_sort_pairs(c, keys, keys_alt, idx, idx_alt, m, key_bits));
+    } else {
+        // deeper than one key word: least significant word first, each pass stable, the permutation carried along
+        ICPB_TRY(devbuf_reserve(c, c->scratch_keys, (size_t)m * sizeof(uint64_t) * 2 * n_words));
+        uint64_t* words = (uint64_t*)c->scratch_keys.p;  // [n_words][m], caller order
+        words_sorted = words + (size_t)n_words * m;
+        morton_keys_kernel<<<kb, 256, 0, s>>>(d_xyz, m, d_root, max_depth, words, idx);
+        c->launches++;
+        for (int w = n_words - 1; w >= 0; --w) {
+            gather_u64_kernel<<<kb, 256, 0, s>>>(words + (size_t)w * m, idx, m, keys);
+            c->launches++;
+            ICPB_TRY(radix_sort_pairs(c, keys, keys_alt, idx, idx_alt, m, 3 * word_levels(w)));
+        }
+        for (int w = 0; w < n_words; ++w) {
+            gather_u64_kernel<<<kb, 256, 0, s>>>(words + (size_t)w * m, idx, m, words_sorted + (size_t)w * m);
+            c->launches++;
+        }
+    }
 
     // sorted points
     if (t.cap_pts < m) {
@@ -650,7 +684,11 @@ static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, i
     uint32_t* offs = (uint32_t*)keys_alt;
     for (;; ++level) {
         const int nb = (int)((count + 127) / 128);
-        node_count_kernel<<<nb, 128, 0, s>>>(t.nodes, first, count, keys, level, max_pts, max_depth, counts);
+        // the key word and the bit position of this level's octant
+        const int w = std::min(level / KEY_LEVELS, n_words - 1);
+        const uint64_t* level_keys = words_sorted ? words_sorted + (size_t)w * m : keys;
+        const int shift = level < max_depth ? 3 * (word_levels(w) - 1 - (level - KEY_LEVELS * w)) : 0;
+        node_count_kernel<<<nb, 128, 0, s>>>(t.nodes, first, count, level_keys, level, max_pts, max_depth, shift, counts);
         c->launches++;
         ICPB_TRY(exclusive_scan_u32(c, counts, offs, count, d_misc + 2));
         uint32_t n_children = 0;
@@ -658,7 +696,7 @@ static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, i
         ICPB_CUDA(c, cudaStreamSynchronize(s));
         const uint32_t next_first = first + count;
         ICPB_TRY(grow_nodes(c, t, (int64_t)next_first + n_children));
-        node_emit_kernel<<<nb, 128, 0, s>>>(t.nodes, first, count, keys, level, max_pts, max_depth, offs, next_first,
+        node_emit_kernel<<<nb, 128, 0, s>>>(t.nodes, first, count, level_keys, level, max_pts, max_depth, shift, offs, next_first,
                                             d_misc + 1, t.parent, t.cell);
         c->launches++;
         t.n_nodes = (int64_t)next_first + n_children;
@@ -868,8 +906,8 @@ int octree_build_device(Ctx* c, const double* d_xyz, int64_t m, int max_pts, int
     c->fast.valid = false;
     c->prev_valid = false;
     if (m <= 0) return ICP_EMPTY_INPUT;
-    if (max_depth < 0 || max_depth > 21 || m > 0x7fffffffLL) {
-        c->err = "octree: max_depth must be in [0,21] and n_tgt < 2^31";
+    if (max_depth < 0 || max_depth > 63 || m > 0x7fffffffLL) {
+        c->err = "octree: max_depth must be in [0,63] and n_tgt < 2^31";
         return ICP_INVALID_ARGUMENT;
     }
     ICPB_TRY(build_tree(c, c->tree, d_xyz, m, max_pts, max_depth, false));

@@ -84,7 +84,6 @@ struct Ctx {
     DeviceOctree fast;  // isotropic search tree over the same points; match positions index ITS point order
     int opt_search_leaf = 4;         // leaf capacity of the search tree
     int opt_search_depth = 16;       // depth cap of the search tree
-    int opt_terminal_pts = 16;       // tile kernel stages subtrees up to this size whole
     int opt_grid_shift = 0;          // entry grid level relative to the median leaf depth
     long long opt_grid_max_cells = 1ll << 32;  // entries (8 B each) over the whole pyramid: up to 32 GiB of the 180 GB
     int opt_grid_levels = 3;         // pyramid height (base level + finer ones)
@@ -116,6 +115,7 @@ struct Ctx {
     double opt_keep_rcap = 0.4;  // mode 5: the ball is widened up to this fraction of the base-level cell edge at most
     DevBuf part_a, part_b;     // per-block partials
     DevBuf scratch0, scratch1, scratch2, scratch3, scratch_src;
+    DevBuf scratch_keys;       // octrees deeper than 21 levels: the extra key words (build.cu)
     DevBuf las_src, las_tgt;   // raw LAS point records of icp_register_las, decoded on the device (cloudio.cu)
     bool src_identity_perm = false;  // resident source is in caller order (no permutation)
     bool prev_valid = false;         // pos / node_io hold last run's matches of the resident source against the current tree
@@ -132,6 +132,7 @@ struct Ctx {
     Mailbox* mail = nullptr;
     Mailbox* peer_mail[MAIL_RANKS] = {};
     bool p2p = false;
+    size_t nn_smem_opt_in = 0;    // nn_kernel's dynamic shared memory opt-in done up to this size (deep octrees)
     bool rs_smem_opt_in = false;  // radix_scatter_kernel's dynamic shared memory opt-in done for this handle's device
     unsigned int mail_epoch = 0;
     unsigned int mail_run = 0;       // sharded runs started on this handle (the same number on every rank): high part of the epoch
@@ -222,7 +223,6 @@ struct NNLaunch {
     double* dist_out;      // distance
     const uint32_t* prev_pos;  // last iteration's match per query, seeds the search (may be null)
     uint32_t* node_io;         // in: node the previous search started from; out: this one's (may be null)
-    uint32_t* tile_node = nullptr;  // mode 2: per-tile start node of the last search (may be null)
     float* lb_io = nullptr;         // mode 4/5: temporal bounds, valid for the positions the queries have on entry (may be null)
     uint4* cand_io = nullptr;       // mode 5: candidates of the last search per query (may be null)
     StatA* part_a;         // per-block partial (may be null: no statistics)

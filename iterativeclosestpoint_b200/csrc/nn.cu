@@ -56,16 +56,13 @@ __device__ __forceinline__ void nn_one_query(const NNArgs& A, const long long i,
         A.oz[i] = qz;
     }
     const bool finite_q = isfinite(qx) && isfinite(qy) && isfinite(qz);
-    uint32_t pp = NONE, pn = NONE;
-    if (A.mode == 1 && A.prev_pos && A.node_io) {
-        pp = A.prev_pos[i];
-        pn = A.node_io[i];
-    } else if (A.mode == 3 && A.prev_pos) {
+    uint32_t pp = NONE;
+    if (A.mode == 3 && A.prev_pos) {
         pp = A.prev_pos[i];
     }
     uint32_t result_node = NONE;
     double best_s;
-    const uint32_t result = per_thread_query<NN_THREADS>(A, qx, qy, qz, finite_q, pp, pn, ICPB_INF, stk, result_node, fell_back,
+    const uint32_t result = per_thread_query<NN_THREADS>(A, qx, qy, qz, finite_q, pp, ICPB_INF, stk, result_node, fell_back,
                                                          false, &best_s);
     // findNearest returns index 0 when nothing was accepted (best_idx = 0 initially, octree.cpp:179)
     const uint32_t pos = (result == NONE) ? A.pos_of_idx0 : result;
@@ -94,7 +91,8 @@ __device__ __forceinline__ void nn_one_query(const NNArgs& A, const long long i,
 }
 
 __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
-    __shared__ uint2 stack[NN_MAX_LEVELS * NN_THREADS];
+    // one stack row per tree level (dynamic: the reference's octree may be up to 63 levels deep, most are 10 - 15)
+    extern __shared__ __align__(16) uint2 stack[];
     __shared__ StatA warp_part[NN_THREADS / 32];
     const long long i = (long long)blockIdx.x * NN_THREADS + threadIdx.x;
     uint2* stk = stack + threadIdx.x;
@@ -149,13 +147,25 @@ __global__ void __launch_bounds__(NN_THREADS) nn_kernel(const NNArgs A) {
 
 int nn_grid_blocks(int64_t n) { return (int)((n + NN_THREADS - 1) / NN_THREADS); }
 
-int nn_tile_launch(Ctx* c, const NNArgs& A);   // nn_tile.cu
 int nn_group_launch(Ctx* c, const NNArgs& A);  // nn_group.cu
 int nn_group_lean_launch(Ctx* c, const NNArgs& A);  // nn_group_lean.cu
 int nn_keep_launch(Ctx* c, const NNArgs& A, int k);  // nn_keep.cu
 
+// shared memory of nn_kernel: one row of NN_THREADS stack entries per level of the deeper of the two trees
+static int nn_stack_bytes(Ctx* c, size_t* bytes) {
+    const int rows = std::max(std::max(c->tree.depth, c->fast.depth) + 3, 8);
+    *bytes = (size_t)rows * NN_THREADS * sizeof(uint2);
+    if (*bytes > 48 * 1024 && *bytes > c->nn_smem_opt_in) {
+        ICPB_CUDA(c, cudaFuncSetAttribute(nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*bytes));
+        c->nn_smem_opt_in = *bytes;
+    }
+    return ICP_OK;
+}
+
 int nn_launch(Ctx* c, const NNLaunch& L_in) {
     NNLaunch L = L_in;
+    size_t stack_bytes = 0;
+    ICPB_TRY(nn_stack_bytes(c, &stack_bytes));
     if (L.mode == 6) L.mode = 4;  // the per-iteration choice between 4 and 5 is run_loop's (api.cu); a stateless query is a plain walk
     if (L.n <= 0) return ICP_OK;
     NNArgs A;
@@ -204,8 +214,6 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
     A.mode = L.mode;
     A.init_best = L.init_best;
     A.pos_of_idx0 = c->fast.pos_of_idx0;
-    A.tile_node = L.tile_node;
-    A.terminal_pts = c->opt_terminal_pts;
     A.worklist = nullptr;
     A.work_count = nullptr;
     A.lb_io = (L.mode >= 4 && c->opt_temporal_skip) ? L.lb_io : nullptr;
@@ -214,7 +222,6 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
     A.walk_alpha = std::max(c->opt_keep_alpha, 1.0);
     A.walk_wmul = std::ldexp(2.0, -c->opt_keep_bias);
     A.walk_rcap = c->opt_keep_rcap * A.gedge[A.gbase];
-    if (L.mode == 2) return nn_tile_launch(c, A);
     const bool in_place5 = L.ox == L.sx && L.oy == L.sy && L.oz == L.sz;
     if (L.mode == 5 && L.prev_pos && A.lb_io && L.cand_io && in_place5 && L.apply_pending && c->d_work_count && c->node_io.p && c->work2.p) {
         // keep what last iteration's candidates and bound prove; search the rest; the per-thread kernel takes what is left
@@ -233,7 +240,7 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
         A.node_io = nullptr;
         A.worklist = A.worklist2;
         A.work_count = c->d_work_count + 1;
-        nn_kernel<<<std::min(nn_grid_blocks(L.n), c->sm_count * 64), NN_THREADS, 0, c->stream>>>(A);
+        nn_kernel<<<std::min(nn_grid_blocks(L.n), c->sm_count * 64), NN_THREADS, stack_bytes, c->stream>>>(A);
         c->launches++;
         ICPB_CUDA(c, cudaGetLastError());
         return ICP_OK;
@@ -278,7 +285,8 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
                 B.gbias_mul = std::ldexp(1.0, -B.gbias);
                 B.apply_pending = 0;
                 B.node_io = nullptr;
-                nn_kernel<<<nn_grid_blocks(B.n), NN_THREADS, 0, fs>>>(B);
+                // (the list is walked with a grid stride: a few waves of blocks are enough however long the chunk is)
+                nn_kernel<<<std::min(nn_grid_blocks(B.n), c->sm_count * 32), NN_THREADS, stack_bytes, fs>>>(B);
                 c->launches++;
                 ICPB_CUDA(c, cudaGetLastError());
             }
@@ -290,7 +298,7 @@ int nn_launch(Ctx* c, const NNLaunch& L_in) {
         }
         A.mode = 3;
     }
-    nn_kernel<<<nn_grid_blocks(L.n), NN_THREADS, 0, c->stream>>>(A);
+    nn_kernel<<<nn_grid_blocks(L.n), NN_THREADS, stack_bytes, c->stream>>>(A);
     c->launches++;
     ICPB_CUDA(c, cudaGetLastError());
     return ICP_OK;

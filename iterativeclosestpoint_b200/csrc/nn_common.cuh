@@ -36,13 +36,11 @@ struct NNArgs {
     const uint32_t* prev_pos;  // last iteration's match per query (may be null)
     uint32_t* node_io;         // in: leaf that held last iteration's match; out: this iteration's (may be null)
     const uint32_t* __restrict__ parent;
-    uint32_t* tile_node;       // tile kernel: per-tile start node of the last search (may be null)
     StatA* part_a;
     const LoopState* state;
     unsigned long long* counters;  // [0] fast-path answers, [1] literal fallbacks, [2] tile lanes sent to the per-thread search,
                                    // [3] candidates scanned by tiles (may be null)
     int apply_pending;
-    int terminal_pts;          // tile kernel: subtrees with at most this many points are staged whole
     int mode;                  // 0: literal traversal from the root; 1: per-thread, climb from the last leaf; 2: warp tiles;
                                // 3: per-thread, entry through the grid cells the search ball touches;
                                // 4: as 3, the candidate scan balanced over the warp (nn_group.cu)
@@ -512,14 +510,15 @@ __device__ __forceinline__ bool cell_walk(const NNArgs& A, const double qx, cons
 }
 
 // ---------------------------------------------------------------------------------------------------
-// One query, one thread: the fast path (temporal or point-location start) with the literal reference traversal
+// One query, one thread: the fast path (cell walk, else a pruned tree search from the deepest node around the query that
+// certainly holds the answer) with the literal reference traversal
 // as fallback.  Returns the sorted target position of the answer (NONE if the reference accepts no point).
-//   pp / pn     last iteration's match and the leaf that held it (NONE if unknown)
+//   pp          last iteration's match (NONE if unknown)
 //   extra_seed  squared distance of some real target point already known (or +inf)
 // ---------------------------------------------------------------------------------------------------
 template <int STRIDE>
 __device__ __forceinline__ uint32_t per_thread_query(const NNArgs& A, const double qx, const double qy, const double qz,
-                                                     const bool finite_q, const uint32_t pp, const uint32_t pn,
+                                                     const bool finite_q, const uint32_t pp,
                                                      const double extra_seed, uint2* stk, uint32_t& result_node,
                                                      bool& fell_back, const bool skip_fast = false, double* best_s = nullptr) {
     uint32_t result = NONE;
@@ -547,51 +546,7 @@ __device__ __forceinline__ uint32_t per_thread_query(const NNArgs& A, const doub
     if (A.mode >= 1 && finite_q && !skip_fast && !walked) {
         double Sd = ICPB_INF;
         uint32_t start = 0;
-        if (pp != NONE && pn != NONE) {
-            // ---- temporal start: last iteration's match seeds the bound, its leaf seeds the start node ----
-            {
-                double px, py, pz;
-                uint32_t pidx;
-                load_point(A.pts, pp, px, py, pz, pidx);
-                Sd = sumsq3(dsub(px, qx), dsub(py, qy), dsub(pz, qz));
-            }
-            Sd = fmin(Sd, extra_seed);
-            const double clear_req = dmul(Sd, 1.0 + 3.637978807091713e-12);  // S (1 + 2^-38)
-            uint32_t n = pn;
-            NodeRegs nd;
-            bool inside_first = false, first = true;
-            for (;;) {  // climb until the query sits inside with enough clearance (the root always qualifies)
-                nd = load_node(A.nodes, n);
-                const double c = fmin(fmin(dsub(qx, nd.lo[0]), dsub(nd.hi[0], qx)),
-                                      fmin(fmin(dsub(qy, nd.lo[1]), dsub(nd.hi[1], qy)), fmin(dsub(qz, nd.lo[2]), dsub(nd.hi[2], qz))));
-                const double cf = (c > 0.0) ? (double)__double2float_rd(c) : 0.0;
-                if (first) inside_first = c >= 0.0;
-                first = false;
-                if (cf * cf > clear_req || n == 0u) break;
-                n = __ldg(A.parent + n);
-            }
-            if (!inside_first) {
-                // the query left last iteration's leaf: walk back down its own cell path while clearance allows
-                for (;;) {
-                    const uint32_t mask = nd.meta & 0xFFu;
-                    if (mask == 0) break;
-                    uint32_t oct = 0;
-                    oct |= (qx > dmul(dadd(nd.lo[0], nd.hi[0]), 0.5)) ? 1u : 0u;
-                    oct |= (qy > dmul(dadd(nd.lo[1], nd.hi[1]), 0.5)) ? 2u : 0u;
-                    oct |= (qz > dmul(dadd(nd.lo[2], nd.hi[2]), 0.5)) ? 4u : 0u;
-                    if (!((mask >> oct) & 1u)) break;
-                    const uint32_t ch = nd.child0 + __popc(mask & ((1u << oct) - 1u));
-                    const NodeRegs cd = load_node(A.nodes, ch);
-                    const double c = fmin(fmin(dsub(qx, cd.lo[0]), dsub(cd.hi[0], qx)),
-                                          fmin(fmin(dsub(qy, cd.lo[1]), dsub(cd.hi[1], qy)), fmin(dsub(qz, cd.lo[2]), dsub(cd.hi[2], qz))));
-                    const double cf = (c > 0.0) ? (double)__double2float_rd(c) : 0.0;
-                    if (!(cf * cf > clear_req)) break;
-                    n = ch;
-                    nd = cd;
-                }
-            }
-            start = n;
-        } else {
+        {
             // ---- point location: walk down the cell path of q, remembering each level's clearance ----
             uint32_t n = 0;
             int level = 0;

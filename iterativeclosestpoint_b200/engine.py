@@ -387,7 +387,7 @@ class ICPEngine:
 
     def stop(self):  # icpengine.cpp:62-66
         self._stop.value = 1
-        self.logMessage.emit("stop requested ...")
+        self.logMessage.emit("用户请求停止配准...")  # icpengine.cpp:65
 
     def getResult(self) -> ICPResult:
         return self.m_result

@@ -367,6 +367,17 @@ class RefEngine(_TreeDumpMixin):
         self.lib.ref_engine_angles(_d(T), C.byref(a), C.byref(t))
         return a.value, t.value
 
+    def last_logs(self) -> list:
+        """logMessage texts of the last run (core/icpengine.h:75), in order."""
+        if not hasattr(self.lib, "ref_engine_last_logs"):
+            return []
+        self.lib.ref_engine_last_logs.restype = C.c_int64
+        self.lib.ref_engine_last_logs.argtypes = [C.c_char_p, C.c_int64]
+        need = self.lib.ref_engine_last_logs(None, 0)
+        buf = C.create_string_buffer(int(need) + 1)
+        self.lib.ref_engine_last_logs(buf, need + 1)
+        return [ln for ln in buf.value.decode("utf-8", "replace").split("\n") if ln != ""]
+
     def icp(self, src, tgt, max_iterations=50, tolerance=1e-6, sigma=3.0, leaf=10, depth=20, stop_after=-1,
             print_logs=False) -> RunResult:
         src = _c3(src).copy() if src is not None else None
@@ -379,6 +390,7 @@ class RefEngine(_TreeDumpMixin):
         rc = self.lib.ref_engine_run(_d(src), n, _d(tgt), m, max_iterations, tolerance, sigma, leaf, depth,
                                      stop_after, C.byref(res), hist, cap, 1 if print_logs else 0)
         out = RunResult()
+        out.logs = self.last_logs()
         out.message = res.finished_msg.decode("utf-8", "replace")
         out.signal_order = res.signal_order.decode()
         out.success = bool(res.success)

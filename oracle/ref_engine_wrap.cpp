@@ -199,6 +199,8 @@ struct ref_result {
     char signal_order[4096];  // compact: s=started i=iteration p=progress f=finished
 };
 
+static std::vector<std::string> g_last_logs;
+
 // Runs ICPEngine::registerPointClouds on copies of the inputs held in reference PointCloud objects;
 // src_xyz receives the (possibly updated) source points afterwards.  A null src/tgt pointer passes a
 // null PointCloud* to the engine; n == 0 passes an empty cloud.
@@ -291,7 +293,23 @@ int ref_engine_run(double* src_xyz, int64_t n_src, const double* tgt_xyz, int64_
     }
     if (print_logs)
         for (const std::string& s : cap.logs) std::printf("%s\n", s.c_str());
+    g_last_logs = cap.logs;
     return ran ? 0 : 1;
+}
+
+// The logMessage texts of the last ref_engine_run, joined with '\n' (UTF-8).  Returns the number of bytes needed.
+int64_t ref_engine_last_logs(char* buf, int64_t cap) {
+    std::string all;
+    for (const std::string& s : g_last_logs) {
+        all += s;
+        all += '\n';
+    }
+    if (buf && cap > 0) {
+        const size_t n = std::min<size_t>(all.size(), (size_t)cap - 1);
+        std::memcpy(buf, all.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)all.size() + 1;
 }
 
 // ICPEngine::computeBestFitTransform on n matched pairs (AoS n x 3 each); T_out row-major 4x4.

@@ -38,7 +38,7 @@ def test_octree_and_nn_match_reference_vectors(handle, name, make, leaf, depth):
         qsets["ties"] = clouds.lattice_tie_queries(tgt)
     for variant, tag in ((VARIANT_ENGINE, "engine"), (VARIANT_CLI, "cli")):
         handle.set_params(ICPParameters(octreeMaxPoints=leaf, octreeMaxDepth=depth), variant)
-        for mode in (0, 1, 2, 3):
+        for mode in (0, 3, 6):
             handle.set_option("nn_mode", mode)
             for qname, q in qsets.items():
                 key = f"nn_{tag}_{qname}"
@@ -48,7 +48,7 @@ def test_octree_and_nn_match_reference_vectors(handle, name, make, leaf, depth):
                 assert np.array_equal(idx, g[key]), f"{name}/{qname}/{tag}/mode{mode}"
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5, 6], ids=["climb", "tile", "walk", "group", "keep", "auto"])
+@pytest.mark.parametrize("mode", [3, 4, 5, 6], ids=["walk", "group", "keep", "auto"])
 @pytest.mark.parametrize("name,make,kw", ENGINE_RUNS, ids=[c[0] for c in ENGINE_RUNS])
 def test_engine_runs_match_reference_vectors(handle, name, make, kw, mode):
     g = load("engine_" + name)
@@ -86,6 +86,29 @@ def test_engine_runs_match_reference_vectors(handle, name, make, kw, mode):
         assert np.max(np.abs(s - g["source_out_sample"])) <= REL_E2E * float(np.max(np.abs(s)))
     else:
         assert np.array_equal(work, src)  # failure exits leave the source untouched
+
+
+@pytest.mark.parametrize("name,make,kw", ENGINE_RUNS, ids=[c[0] for c in ENGINE_RUNS])
+def test_engine_log_lines_are_the_references(handle, name, make, kw):
+    """logMessage is part of the boundary (core/icpengine.h:75): the texts the C ABI hands to the log callback are the
+    reference's own, line for line (captured from the compiled reference by tools/make_golden.py).  The one line that
+    ICPEngine::stop() itself emits (icpengine.cpp:65) belongs to the adapters' stop(), not to the run."""
+    g = load("engine_" + name)
+    want = [ln for ln in str(g["logs"]).split("\n") if ln and ln != "用户请求停止配准..."]
+    src, tgt = make()
+    kw = dict(kw)
+    stop_after = kw.pop("stop_after", -1)
+    handle.set_params(ICPParameters(maxIterations=kw.get("max_iterations", 50), tolerance=kw.get("tolerance", 1e-6),
+                                    sigmaMultiplier=kw.get("sigma", 3.0), octreeMaxPoints=kw.get("leaf", 10),
+                                    octreeMaxDepth=kw.get("depth", 20)), VARIANT_ENGINE)
+    lines, seen = [], []
+    import ctypes as C
+    flag = C.c_int(0)
+    handle.set_callbacks(on_iteration=lambda r: (seen.append(r.iteration), setattr(flag, "value", 1 if 0 <= stop_after <= len(seen) else 0)),
+                         on_log=lines.append)
+    handle.register(src.copy(), tgt, stop_flag=flag if stop_after >= 0 else None)
+    assert len(want) > 5
+    assert lines == want
 
 
 @pytest.mark.parametrize("name,make,kw", CLI_RUNS, ids=[c[0] for c in CLI_RUNS])
