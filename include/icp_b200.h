@@ -9,8 +9,10 @@
  * Conventions
  *   - Point arrays are AoS `double xyz[n][3]`, i.e. exactly `std::vector<Point3D>::data()`
  *     (PointCloudRegistration/core/pointcloud.h:12-23: struct Point3D { double x, y, z; }).
- *   - 4x4 transforms are ROW-major double[16] (the reference's Eigen::Matrix4d is column-major; the C++
- *     adapter in icp_b200_engine.hpp converts).
+ *   - 4x4 transforms are ROW-major double[16] everywhere, in this header and in the C++ adapter (icp_b200_engine.hpp:
+ *     Mat4 = std::array<double,16>, row-major).  The reference's Eigen::Matrix4d is column-major: a caller that wants one
+ *     maps it with  Eigen::Map<const Eigen::Matrix<double,4,4,Eigen::RowMajor>>(m.data())  (assigning the 16 doubles to a
+ *     Matrix4d unchanged would give the transpose).
  *   - All functions return an icp_status; ICP_OK == 0.  Nothing throws, nothing falls back to the CPU:
  *     without a usable CUDA device every call fails with ICP_CUDA_ERROR.
  *   - A handle is bound to one CUDA device and is not re-entrant (the reference engine is not either:
@@ -54,7 +56,7 @@ typedef enum icp_variant {
 typedef struct icp_params {
     int32_t max_iterations;     /* maxIterations   = 50   */
     int32_t octree_max_points;  /* octreeMaxPoints = 10   */
-    int32_t octree_max_depth;   /* octreeMaxDepth  = 20 ; 1..21 supported (3 bits/level in a 64-bit key) */
+    int32_t octree_max_depth;   /* octreeMaxDepth  = 20 ; 0..63 accepted (the reference's GUI offers 10..50) */
     int32_t variant;            /* icp_variant */
     double tolerance;           /* tolerance       = 1e-6 */
     double sigma_multiplier;    /* sigmaMultiplier = 3.0  */

@@ -1215,6 +1215,34 @@ int icp_comm_destroy(icp_handle h) {
 // fraction of one SM busy), so the batch is spread over a pool of worker handles -- one CUDA stream each on the
 // same device, driven by one host thread each -- and the GPU overlaps their kernels.  Every pair goes through the
 // ordinary single-pair path (register_impl), so batch results are the single-pair results by construction.
+// everything icp_set_params / icp_set_option can change, from the handle that owns a batch to one of its workers
+static void copy_options(Ctx* w, const Ctx* c) {
+    w->params = c->params;
+    w->opt_nn_mode = c->opt_nn_mode;
+    w->opt_order_queries = c->opt_order_queries;
+    w->opt_write_mask = c->opt_write_mask;
+    w->opt_count = c->opt_count;
+    w->opt_temporal_skip = c->opt_temporal_skip;
+    w->opt_nn_chunks = c->opt_nn_chunks;
+    w->opt_keep_k = c->opt_keep_k;
+    w->opt_keep_alpha = c->opt_keep_alpha;
+    w->opt_keep_bias = c->opt_keep_bias;
+    w->opt_keep_enter = c->opt_keep_enter;
+    w->opt_keep_exit = c->opt_keep_exit;
+    w->opt_keep_rcap = c->opt_keep_rcap;
+    w->opt_search_leaf = c->opt_search_leaf;
+    w->opt_search_depth = c->opt_search_depth;
+    w->opt_grid_shift = c->opt_grid_shift;
+    w->opt_grid_max_cells = c->opt_grid_max_cells;
+    w->opt_grid_levels = c->opt_grid_levels;
+    w->opt_grid_coarse = c->opt_grid_coarse;
+    w->opt_base_occupancy = c->opt_base_occupancy;
+    w->opt_range_max = c->opt_range_max;
+    w->opt_walk_bias = c->opt_walk_bias;
+    w->opt_walk_max_cells = c->opt_walk_max_cells;
+    w->opt_lookahead = c->opt_lookahead;
+}
+
 int icp_register_batch(icp_handle h, int32_t n_pairs, double* const* src_xyz, const int64_t* n_src, const double* const* tgt_xyz,
                        const int64_t* n_tgt, icp_result* results) {
     Ctx* c = (Ctx*)h;
@@ -1246,13 +1274,13 @@ int icp_register_batch(icp_handle h, int32_t n_pairs, double* const* src_xyz, co
         if (!small.empty()) {
             // chunks of a few waves of blocks, spread over up to three lanes (this handle + two workers, one host
             // thread and one stream each): while one lane's kernel runs, the others pack / copy / unpack
-            const int rec_cap = c->params.max_iterations + 1;
+            const int rec_cap = std::max(c->params.max_iterations, 0) + 1;
             const int chunk = std::max(c->sm_count * 2, 64);
             const int n_chunks = ((int)small.size() + chunk - 1) / chunk;
             const int lanes = std::min(3, n_chunks);
             if (lanes > 1) ICPB_TRY(ensure_workers(lanes - 1));
             std::vector<std::vector<int32_t>> redo((size_t)lanes);
-            std::atomic<int> next_chunk{0};
+            std::atomic<int> next_chunk{0}, fatal_lane{-1};
             auto lane_fn = [&](int lane) {
                 Ctx* w = (lane == 0) ? c : c->workers[(size_t)lane - 1];
                 cudaSetDevice(w->device);
@@ -1270,8 +1298,8 @@ int icp_register_batch(icp_handle h, int32_t n_pairs, double* const* src_xyz, co
                     const int s = small_batch_run(w, part, src_xyz, n_src, tgt_xyz, n_tgt, recs, rec_cap, n_rec, exit_code, flagged, moved,
                                                   src_off);
                     if (s != ICP_OK) {
-                        if (w != c) c->err = w->err;
-                        fatal.store(s);
+                        int none = ICP_OK;
+                        if (fatal.compare_exchange_strong(none, s)) fatal_lane.store(lane);  // the first failure reports
                         break;
                     }
                     for (size_t k = 0; k < part.size(); ++k) {
@@ -1296,7 +1324,11 @@ int icp_register_batch(icp_handle h, int32_t n_pairs, double* const* src_xyz, co
             for (int l = 1; l < lanes; ++l) lane_threads.emplace_back(lane_fn, l);
             lane_fn(0);
             for (auto& t : lane_threads) t.join();
-            if (fatal.load() != ICP_OK) return fatal.load();
+            if (fatal.load() != ICP_OK) {
+                const int fl = fatal_lane.load();
+                if (fl > 0) c->err = c->workers[(size_t)fl - 1]->err;  // (lane 0 is this handle: its message is already here)
+                return fatal.load();
+            }
             for (auto& r : redo) todo.insert(todo.end(), r.begin(), r.end());
         }
     }
@@ -1305,19 +1337,19 @@ int icp_register_batch(icp_handle h, int32_t n_pairs, double* const* src_xyz, co
     const int want = std::max(1, std::min(std::min(c->opt_batch_workers, n_todo), 64));
     ICPB_TRY(ensure_workers(want));
     std::atomic<int32_t> next{0};
+    std::atomic<int> fatal_worker{-1};
 
-    auto run = [&](Ctx* w) {
+    auto run = [&](Ctx* w, int wi) {
         cudaSetDevice(w->device);
-        w->params = c->params;
-        w->opt_nn_mode = c->opt_nn_mode;
-        w->opt_order_queries = c->opt_order_queries;
+        copy_options(w, c);  // a pair that takes the general path runs with this handle's tuning
         for (;;) {
             const int32_t q = next.fetch_add(1);
             if (q >= n_todo || fatal.load() != ICP_OK) break;
             const int32_t p = todo[(size_t)q];
             const int s = register_impl(w, src_xyz[p], n_src[p], n_src[p], tgt_xyz[p], n_tgt[p], &results[p], nullptr);
             if (s == ICP_CUDA_ERROR || s == ICP_NCCL_ERROR) {
-                fatal.store(s);
+                int none = ICP_OK;
+                if (fatal.compare_exchange_strong(none, s)) fatal_worker.store(wi);
                 break;
             }
             int expect = ICP_OK;
@@ -1325,12 +1357,12 @@ int icp_register_batch(icp_handle h, int32_t n_pairs, double* const* src_xyz, co
         }
     };
     std::vector<std::thread> threads;
-    for (int k = 1; k < want; ++k) threads.emplace_back(run, c->workers[(size_t)k]);
-    run(c->workers[0]);
+    for (int k = 1; k < want; ++k) threads.emplace_back(run, c->workers[(size_t)k], k);
+    run(c->workers[0], 0);
     for (auto& t : threads) t.join();
     for (Ctx* w : c->workers) c->launches += w->launches, w->launches = 0;
     if (fatal.load() != ICP_OK) {
-        c->err = "batch: a worker failed: " + c->workers[0]->err;
+        c->err = "batch: a worker failed: " + c->workers[(size_t)std::max(fatal_worker.load(), 0)]->err;
         return fatal.load();
     }
     return worst.load();

@@ -301,7 +301,13 @@ int icp_las_write(icp_handle h, const char* path, const double* xyz, int64_t n, 
     Ctx* c = (Ctx*)h;
     if (!c || !path) return ICP_INVALID_ARGUMENT;
     if (n <= 0 || !xyz) return ICP_EMPTY_INPUT;
-    std::vector<uint8_t> image((size_t)(ICP_LAS_HEADER_BYTES + (int64_t)ICP_LAS_RECORD_BYTES * n));
+    std::vector<uint8_t> image;
+    try {  // (nothing may throw across the C boundary)
+        image.resize((size_t)(ICP_LAS_HEADER_BYTES + (int64_t)ICP_LAS_RECORD_BYTES * n));
+    } catch (...) {
+        c->err = "out of host memory for the LAS file image";
+        return ICP_IO_ERROR;
+    }
     int64_t bytes = 0;
     ICPB_TRY(icp_las_file_image(h, xyz, n, variant, scale3, offset3, image.data(), (int64_t)image.size(), &bytes));
     FILE* f = std::fopen(path, "wb");
@@ -363,8 +369,25 @@ int icp_las_read(icp_handle h, const char* path, int64_t max_points, int variant
         std::fclose(f);
         return ICP_INVALID_ARGUMENT;
     }
-    std::vector<uint8_t> rec((size_t)n * H.record_length);
-    bool ok = std::fseek(f, (long)H.offset_to_data, SEEK_SET) == 0;
+    // the header's word is not taken for the file's size: a corrupt count must not drive the allocation
+    bool ok = std::fseek(f, 0, SEEK_END) == 0;
+    const long long file_bytes = ok ? (long long)std::ftell(f) : -1;
+    if (file_bytes < 0 || (long long)H.offset_to_data + (long long)n * (long long)H.record_length > file_bytes) {
+        std::fclose(f);
+        *n_out = 0;
+        c->err = std::string("truncated LAS point data in ") + path;
+        return ICP_IO_ERROR;
+    }
+    std::vector<uint8_t> rec;
+    try {
+        rec.resize((size_t)n * H.record_length);
+    } catch (...) {
+        std::fclose(f);
+        *n_out = 0;
+        c->err = "out of host memory for the LAS point records";
+        return ICP_IO_ERROR;
+    }
+    ok = std::fseek(f, (long)H.offset_to_data, SEEK_SET) == 0;
     ok = ok && std::fread(rec.data(), 1, rec.size(), f) == rec.size();
     std::fclose(f);
     if (!ok) {
@@ -382,7 +405,11 @@ int icp_downsample(icp_handle h, const double* xyz, int64_t n, int32_t target_si
     *n_out = 0;
     if (n <= 0 || !xyz || target_size <= 0) return ICP_EMPTY_INPUT;  // pointcloud.cpp:109-111 returns nullptr
     if (!xyz_out) return ICP_INVALID_ARGUMENT;
-    if ((int32_t)n <= target_size) {  // pointcloud.cpp:117-118: copy
+    if (n > 0x7fffffffLL) {  // the reference's sizes are ints (pointcloud.cpp:113)
+        c->err = "downsample: more than 2^31 - 1 points";
+        return ICP_INVALID_ARGUMENT;
+    }
+    if (n <= (int64_t)target_size) {  // pointcloud.cpp:117-118: copy
         std::memcpy(xyz_out, xyz, (size_t)n * 3 * sizeof(double));
         *n_out = n;
         return ICP_OK;

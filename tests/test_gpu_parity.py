@@ -459,6 +459,23 @@ def test_register_batch_matches_the_oracle(handle, oracle, small):
     assert np.max(np.abs(single - srcs[3])) <= 1e-12 * float(np.max(np.abs(single)))
 
 
+def test_register_batch_256_pairs_of_config5_against_the_oracle(handle, oracle):
+    """BASELINE.json config #5 as specified (2000 <-> 2000 points per pair, per-pair octrees in the reference), 256 pairs through
+    one icp_register_batch call: every pair against the oracle's whole run (iteration counts, inlier counts, transforms within
+    1e-9, moved sources)."""
+    from concurrent.futures import ThreadPoolExecutor
+    pairs = [synth.small_pair(p) for p in range(256)]
+    srcs = [s.copy() for s, _ in pairs]
+    handle.set_params(ICPParameters())
+    results = handle.register_batch(srcs, [t for _, t in pairs])
+    with ThreadPoolExecutor(oracle.hw_threads()) as ex:
+        wants = list(ex.map(lambda st: oracle.icp(st[0], st[1]), pairs))
+    assert sum(r.totalIterations for r in results) > 256 * 4
+    for k, (moved, r, want) in enumerate(zip(srcs, results, wants)):
+        _check_run(r, want, len(pairs[k][0]))
+        assert np.max(np.abs(moved - want.source_out)) <= 1e-9 * float(np.max(np.abs(want.source_out))), k
+
+
 def test_register_batch_failure_exits(handle, oracle):
     tiny_s = np.array([[0.0, 0, 0], [1.0, 0, 0]]); tiny_t = np.array([[0, 0, 0.1], [1, 0, 0.1], [0, 1, 0.1]], dtype=np.float64)
     ok_s, ok_t = synth.small_pair(7, n=600)
