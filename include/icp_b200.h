@@ -131,15 +131,18 @@ void icp_default_params(icp_params* p);                         /* ICPParameters
 int icp_set_callbacks(icp_handle h, icp_iteration_cb on_iteration, icp_progress_cb on_progress, icp_log_cb on_log,
                       void* user);
 /* Tuning knobs that never change results (every search mode returns the reference's indices):
- *   "nn_mode"  0 literal reference traversal from the root, one query per thread; 1 per-thread climbing search;
- *              2 warp tiles with shared-memory staged candidates; 3 per-thread walk over the entry-grid cells the search
- *              ball touches; 4 the same walk with the candidate scan balanced over the warp; 5 keep / collect: candidates
- *              and a lower bound carried between iterations settle a query without a search; 6 (default) mode 4 while
- *              the registration moves, mode 5 once it has nearly converged -- all with the literal traversal as fallback;
+ *   "nn_mode"  0 literal reference traversal from the root, one query per thread; 3 per-thread walk over the entry-grid
+ *              cells the search ball touches (a pruned tree search where the walk does not apply); 4 the same walk with the
+ *              candidate scan balanced over the warp; 5 keep / collect: candidates and a lower bound carried between
+ *              iterations settle a query without a search; 6 (default) mode 4 while the registration moves, mode 5 once it
+ *              has nearly converged -- all with the literal traversal as fallback.  (1 and 2, the climbing search as a
+ *              mode of its own and the warp-tile kernel, lost and were retired: ICP_INVALID_ARGUMENT.)
  *   "keep_k" "keep_alpha" "keep_rcap" "keep_bias" "keep_enter" "keep_exit"   the keep / collect path (modes 5, 6);
  *   "grid_levels" "grid_coarse" "grid_max_cells" "grid_shift" "base_occupancy" "range_max"   the entry-grid pyramid;
- *   "search_leaf" "search_depth" "terminal_pts" "walk_bias" "walk_max_cells" "nn_chunks" "temporal_skip"   search details;
+ *   "search_leaf" "search_depth" "walk_bias" "walk_max_cells" "nn_chunks" "temporal_skip"   search details;
  *   "order_queries" (Morton-order the source internally, default 1), "write_mask" (keep the inlier mask),
+ *   "lookahead" (iterations enqueued before the host reads their records, modes 0 and 3 without callbacks / stop flag),
+ *   "redistribute" "shard_target" (sharded runs: spatial re-deal of the source shards and 1/R target upload, default 1),
  *   "batch_small" "batch_workers" (icp_register_batch: one-block kernel for small pairs, worker streams), "count" (profiling
  *   counters). */
 int icp_set_option(icp_handle h, const char* key, double value);
@@ -190,7 +193,13 @@ int icp_comm_unique_id(icp_handle h, void* unique_id_128);
 int icp_comm_init(icp_handle h, int rank, int n_ranks, const void* unique_id_128);
 int icp_comm_destroy(icp_handle h);
 /* icp_register on this rank's shard of the source; `n_src_global` is the total source size (the N of
- * the mean / variance).  All ranks return identical results (rank-ordered summation of the gathered partials). */
+ * the mean / variance).  All ranks return identical results (rank-ordered summation of the gathered partials).
+ * COLLECTIVE: every rank calls it the same number of times, with the same target and parameters.  Inside, each rank
+ * uploads 1/R of the target (an all-gather over NVLink hands every replica the rest) and the ranks re-deal the source
+ * points by region over NVLink (a range of the caller's order says nothing about where its points are); the moved points
+ * travel home before the write-back, so the caller gets ITS shard back in ITS order.  A stop flag raised on any rank ends
+ * the run on every rank in the same iteration (ICP_CANCELLED, sources untouched).  icp_source_upload /
+ * icp_register_resident on a handle with a communicator behave the same way. */
 int icp_register_sharded(icp_handle h, double* src_shard_xyz, int64_t n_shard, int64_t n_src_global,
                          const double* tgt_xyz, int64_t n_tgt, icp_result* out, const volatile int* stop_flag);
 
@@ -201,8 +210,8 @@ int icp_register_batch(icp_handle h, int32_t n_pairs, double* const* src_xyz, co
 /* How many queries since the last reset were answered by the order-independent fast path and how many
  * had to be re-run through the literal reference traversal (exact ties / duplicates / 1-ulp near ties). */
 int icp_nn_counters(icp_handle h, int64_t* fast_path, int64_t* literal_fallback, int reset);
-/* Tile kernel (nn_mode 2): lanes a tile could not prove and handed to the per-thread search, and the number of
- * (tile, candidate) pairs scanned -- candidates per query = candidates_scanned / queries. */
+/* Balanced kernels (nn_mode 4 - 6): queries handed to the per-thread search, and the number of candidates scanned
+ * (profiling counters, maintained only with the "count" option). */
 int icp_nn_tile_counters(icp_handle h, int64_t* per_thread_lanes, int64_t* candidates_scanned, int reset);
 
 /* ---- data formats either side of the loop ------------------------------------ */

@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from iterativeclosestpoint_b200 import sharding, synth  # noqa: E402
+import shard_merge  # noqa: E402  (tests/shard_merge.py)
 
 
 def test_shard_ranges_tile_the_source():
@@ -68,10 +69,10 @@ def test_spatial_shards_partition_the_cloud_into_compact_equal_parts():
 def test_rank_ordered_merge_matches_whole_cloud_statistics():
     r = np.random.default_rng(0)
     d = np.abs(r.normal(size=100_003)) * 0.3
-    whole = sharding.stat_partial(d)
+    whole = shard_merge.stat_partial(d)
     for world in (2, 3, 8):
-        parts = [sharding.stat_partial(d[slice(*sharding.shard_range(len(d), k, world))]) for k in range(world)]
-        m = sharding.merge_in_rank_order(parts)
+        parts = [shard_merge.stat_partial(d[slice(*sharding.shard_range(len(d), k, world))]) for k in range(world)]
+        m = shard_merge.merge_in_rank_order(parts)
         assert m[0] == whole[0] and m[3] == whole[3] and m[4] == whole[4]
         assert abs(m[1] - whole[1]) <= 1e-14 * whole[1] and abs(m[2] - whole[2]) <= 1e-12 * whole[2]
 
@@ -107,14 +108,14 @@ def _worker(rank, world, port, q):
         dv = src[lo:hi] - tgt[idx]
         d = np.sqrt(dv[:, 0] * dv[:, 0] + dv[:, 1] * dv[:, 1] + dv[:, 2] * dv[:, 2])
         gathered = [None] * world
-        dist.all_gather_object(gathered, sh.stat_partial(d))
-        merged = sh.merge_in_rank_order(gathered)
-        mean, std, thr = sh.threshold(merged, len(src), 3.0, 0)
+        dist.all_gather_object(gathered, shard_merge.stat_partial(d))
+        merged = shard_merge.merge_in_rank_order(gathered)
+        mean, std, thr = shard_merge.threshold(merged, len(src), 3.0, 0)
         pa = pb = (tgt.min(0) + tgt.max(0)) * 0.5
         gathered_b = [None] * world
-        dist.all_gather_object(gathered_b, sh.moment_partial(src[lo:hi], tgt[idx], d, thr, pa, pb))
-        mom = sh.sum_in_rank_order(gathered_b)
-        cA, cB, H = sh.moments_to_H(mom, pa, pb)
+        dist.all_gather_object(gathered_b, shard_merge.moment_partial(src[lo:hi], tgt[idx], d, thr, pa, pb))
+        mom = shard_merge.sum_in_rank_order(gathered_b)
+        cA, cB, H = shard_merge.moments_to_H(mom, pa, pb)
         T = orc.solve_from_H(H, cA, cB)
         q.put((rank, merged.tobytes(), float(thr), mom.tobytes(), T.tobytes(), (d <= thr).astype(np.uint8).tobytes(), lo, hi))
     finally:
