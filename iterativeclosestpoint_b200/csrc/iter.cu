@@ -319,7 +319,11 @@ __device__ __forceinline__ void sum_partials_fixed(const double* part, int n_par
 // partials -- identical arithmetic in every block and on every rank -- then owns block-strided tiles (fixed
 // geometry => fixed summation order).  The last block to finish sums the block partials in index order into this
 // rank's slot and, on a single-rank run, goes straight on to the solve.
-__global__ void __launch_bounds__(RED_THREADS, 2) stage_b_kernel(const double* __restrict__ sx, const double* __restrict__ sy,
+#ifndef STAGEB_UNR
+#define STAGEB_UNR 4
+#define STAGEB_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(RED_THREADS, STAGEB_BLOCKS) stage_b_kernel(const double* __restrict__ sx, const double* __restrict__ sy,
                                                               const double* __restrict__ sz, const uint32_t* __restrict__ pos,
                                                               const double* __restrict__ dist, int64_t n,
                                                               const TPoint* __restrict__ pts, LoopState* __restrict__ st,
@@ -357,9 +361,11 @@ __global__ void __launch_bounds__(RED_THREADS, 2) stage_b_kernel(const double* _
     }
     AccB acc;
     accb_zero(acc);
-    // four tiles per trip: the four (distance, match) loads and then the four gathers are in flight together; the order
-    // in which a thread adds its queries is still fixed by the launch geometry alone
-    constexpr int UNR = 4;
+    // UNR tiles per trip: the (distance, match) loads, then the gathers of the matched points and the query loads, are in
+    // flight together; the order in which a thread adds its queries is still fixed by the launch geometry alone.  Everything
+    // stays in registers: the loads are unconditional (an outlier's slot reads point 0 and is not added), so no predicated
+    // array element forces the compiler into local memory.
+    constexpr int UNR = STAGEB_UNR;
     const int64_t stride = (int64_t)gridDim.x * RED_THREADS;
     for (int64_t base = (int64_t)blockIdx.x * RED_THREADS; base < n; base += stride * UNR) {
         double d[UNR];
@@ -368,26 +374,26 @@ __global__ void __launch_bounds__(RED_THREADS, 2) stage_b_kernel(const double* _
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int64_t i = base + u * stride + threadIdx.x;
-            d[u] = (i < n) ? dist[i] : 0.0;
-            p[u] = (i < n) ? pos[i] : 0xFFFFFFFFu;
+            d[u] = (i < n) ? __ldg(dist + i) : 0.0;
+            p[u] = (i < n) ? __ldg(pos + i) : 0xFFFFFFFFu;
         }
-        double ax[UNR], ay[UNR], az[UNR];
-        TPoint t[UNR];
+        double ax[UNR], ay[UNR], az[UNR], bx[UNR], by[UNR], bz[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int64_t i = base + u * stride + threadIdx.x;
             ok[u] = (i < n) && (d[u] <= thr) && (p[u] != 0xFFFFFFFFu);  // icpengine.cpp:264-268 (NaN => outlier)
             if (mask_out && i < n) mask_out[i] = ok[u] ? 1 : 0;
-            if (ok[u]) {
-                t[u] = pts[p[u]];
-                ax[u] = sx[i];
-                ay[u] = sy[i];
-                az[u] = sz[i];
-            }
+            const int64_t iq = ok[u] ? i : 0;
+            const uint32_t ip = ok[u] ? p[u] : 0u;
+            long long w;
+            asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=d"(bx[u]), "=d"(by[u]), "=d"(bz[u]), "=l"(w) : "l"(pts + ip));
+            ax[u] = __ldg(sx + iq);
+            ay[u] = __ldg(sy + iq);
+            az[u] = __ldg(sz + iq);
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u)
-            if (ok[u]) accb_add_pair(acc, d[u], ax[u], ay[u], az[u], t[u].x, t[u].y, t[u].z, pa, pb);
+            if (ok[u]) accb_add_pair(acc, d[u], ax[u], ay[u], az[u], bx[u], by[u], bz[u], pa, pb);
     }
     accb_block_reduce(acc, part + (int64_t)blockIdx.x * STATB_DOUBLES);
     __syncthreads();

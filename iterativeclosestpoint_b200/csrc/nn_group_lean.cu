@@ -22,7 +22,10 @@ namespace icpb {
 
 constexpr int GW_THREADS = 128;
 constexpr int GW_WARPS = GW_THREADS / 32;
-constexpr int GW_QCAP = 256;  // scan items per warp
+#ifndef GWL_QCAP
+#define GWL_QCAP 256
+#endif
+constexpr int GW_QCAP = GWL_QCAP;  // scan items per warp
 constexpr int GW_SUB = 8;     // points per scan item (two batches of four loads in flight)
 
 struct __align__(16) GlSlot {
