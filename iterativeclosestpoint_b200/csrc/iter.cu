@@ -66,8 +66,8 @@ __device__ __forceinline__ void moma_push(MomA& a, double d, double p) {
     a.s1 += t;
     a.s2 += t * t;
     if (isfinite(d)) {
-        a.dmin = fmin(a.dmin, d);
-        a.dmax = fmax(a.dmax, d);
+        a.dmin = d < a.dmin ? d : a.dmin;
+        a.dmax = d > a.dmax ? d : a.dmax;
     } else {
         a.problems += 1.0;
     }
@@ -119,13 +119,13 @@ __global__ void __launch_bounds__(RED_THREADS) stat_a_kernel(const double* __res
     MomA acc;
     acc.n = 0.0; acc.s1 = 0.0; acc.s2 = 0.0; acc.dmin = DBL_MAX; acc.dmax = 0.0; acc.problems = 0.0;
     int64_t i = b + threadIdx.x;
-    for (; i + 3 * RED_THREADS < e; i += 4 * RED_THREADS) {
-        const double d0 = dist[i], d1 = dist[i + RED_THREADS], d2 = dist[i + 2 * RED_THREADS], d3 = dist[i + 3 * RED_THREADS];
-        moma_push(acc, d0, p);
-        moma_push(acc, d1, p);
-        moma_push(acc, d2, p);
-        moma_push(acc, d3, p);
-        acc.n += 4.0;
+    for (; i + 7 * RED_THREADS < e; i += 8 * RED_THREADS) {  // eight loads in flight per thread
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(dist + i + u * RED_THREADS);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) moma_push(acc, v[u], p);
+        acc.n += 8.0;
     }
     for (; i < e; i += RED_THREADS) {
         moma_push(acc, dist[i], p);
