@@ -22,11 +22,7 @@ namespace icpb {
 
 constexpr int GW_THREADS = 128;
 constexpr int GW_WARPS = GW_THREADS / 32;
-constexpr int GW_QCAP_WALK = 256;  // scan items per warp, iterations that start from last iteration's matches
-constexpr int GW_QCAP_SEED = 512;  // ... first iteration / stateless queries: the seed from the query's own base cell is loose, half of
-                                   // the balls need the next coarser level and four times the candidates (0.86 M of 10 M queries overflowed
-                                   // a 256-item queue and took the per-thread search, 0.53 M with 512; for the later iterations the
-                                   // larger queue costs more in occupancy than it saves)
+constexpr int GW_QCAP = 256;  // scan items per warp
 constexpr int GW_SUB = 8;     // points per scan item (two batches of four loads in flight)
 
 struct __align__(16) GlSlot {
@@ -37,11 +33,7 @@ struct __align__(16) GlSlot {
 // iterations run the instance without that code (a fifth of the kernel's instructions, never executed there: less pressure on
 // the instruction cache); a query that has no match then simply goes on the work list.
 template <bool SEED>
-#ifndef GWL_MINBLOCKS
-#define GWL_MINBLOCKS 7
-#endif
-__global__ void __launch_bounds__(GW_THREADS, GWL_MINBLOCKS) nn_group_lean_kernel(const NNArgs A) {
-    constexpr int GW_QCAP = SEED ? GW_QCAP_SEED : GW_QCAP_WALK;
+__global__ void __launch_bounds__(GW_THREADS) nn_group_lean_kernel(const NNArgs A) {
     __shared__ GlSlot slot_all[GW_WARPS][32];
     __shared__ uint2 queue_all[GW_WARPS][GW_QCAP];   // item: x = first point, y = count | owner lane << 8; result: x = position, y = tie
     __shared__ double rbest_all[GW_WARPS][GW_QCAP];  // result: smallest s of the item
@@ -131,109 +123,100 @@ __global__ void __launch_bounds__(GW_THREADS, GWL_MINBLOCKS) nn_group_lean_kerne
         }
     }
 
-    // ---- B. queue the scan items (a lane's items are consecutive), scan them round-robin; C. merge the own items ----
-    // The queue holds GW_QCAP items.  Where the cloud is dense a warp's 32 queries bring more than that (a third of the work
-    // list of the per-thread kernel used to be lanes that did not fit): the lanes are then served in ROUNDS -- every round takes
-    // the leading pending lanes whose items fit together, scans, merges, and leaves the rest for the next round.
+    // ---- B. queue the scan items (a lane's items are consecutive), then scan them round-robin ----
     uint32_t nsub = 0;
     if (elig) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) nsub += (ecnt[c] + GW_SUB - 1) / GW_SUB;
-        if (nsub > (uint32_t)GW_QCAP) elig = false;  // one query with more candidates than a whole queue: per-thread search
     }
-    bool settled = false;
-    bool waiting = elig;
-    for (;;) {
-        uint32_t off_end = waiting ? nsub : 0u;
+    uint32_t off_end = nsub;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(FULL, off_end, o);
-            if (lane >= o) off_end += v;
-        }
-        const uint32_t off_begin = off_end - (waiting ? nsub : 0u);
-        const bool go = waiting && off_end <= (uint32_t)GW_QCAP;  // (the first waiting lane always fits)
-        if (!__any_sync(FULL, go)) break;
-        const uint32_t total = __reduce_max_sync(FULL, go ? off_end : 0u);
-        if (go) {
-            uint32_t o = off_begin;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, off_end, o);
+        if (lane >= o) off_end += v;
+    }
+    const uint32_t off_begin = off_end - nsub;
+    const bool fits = off_end <= (uint32_t)GW_QCAP;
+    if (!fits) elig = false;
+    const uint32_t total = __reduce_max_sync(FULL, fits ? off_end : 0u);
+    if (elig) {
+        uint32_t o = off_begin;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                for (uint32_t k = 0; k < ecnt[c]; k += GW_SUB) {
-                    const uint32_t m = ecnt[c] - k;
-                    queue[o++] = make_uint2(ept[c] + k, (m < (uint32_t)GW_SUB ? m : (uint32_t)GW_SUB) | ((uint32_t)lane << 8));
-                }
+        for (int c = 0; c < 8; ++c) {
+            for (uint32_t k = 0; k < ecnt[c]; k += GW_SUB) {
+                const uint32_t m = ecnt[c] - k;
+                queue[o++] = make_uint2(ept[c] + k, (m < (uint32_t)GW_SUB ? m : (uint32_t)GW_SUB) | ((uint32_t)lane << 8));
             }
-            GlSlot s;
-            s.qx = qx; s.qy = qy; s.qz = qz; s.bound = bound;
-            slot[lane] = s;
         }
-        __syncwarp();
-        for (uint32_t base = 0; base < total; base += 32) {
-            const uint32_t j = base + lane;
-            const bool has = j < total;
-            const uint2 it = has ? queue[j] : make_uint2(0u, 0u);
-            const uint32_t cnt = it.y & 0xFFu;
-            const GlSlot s = slot[(it.y >> 8) & 31u];
-            double best = ICPB_INF, second = ICPB_INF;
-            uint32_t bpos = NONE;
-            const bool second_batch = __any_sync(FULL, cnt > 4u);
+        GlSlot s;
+        s.qx = qx; s.qy = qy; s.qz = qz; s.bound = bound;
+        slot[lane] = s;
+    }
+    __syncwarp();
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t j = base + lane;
+        const bool has = j < total;
+        const uint2 it = has ? queue[j] : make_uint2(0u, 0u);
+        const uint32_t cnt = it.y & 0xFFu;
+        const GlSlot s = slot[(it.y >> 8) & 31u];
+        double best = ICPB_INF, second = ICPB_INF;
+        uint32_t bpos = NONE;
+        const bool second_batch = __any_sync(FULL, cnt > 4u);
 #pragma unroll
-            for (int b = 0; b < GW_SUB; b += 4) {
-                if (b == 0 || second_batch) {
-                    double px[4], py[4], pz[4];
+        for (int b = 0; b < GW_SUB; b += 4) {
+            if (b == 0 || second_batch) {
+                double px[4], py[4], pz[4];
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        px[t] = py[t] = pz[t] = 0.0;
-                        uint32_t pidx;
-                        if ((uint32_t)(b + t) < cnt) load_point(A.pts, it.x + (uint32_t)(b + t), px[t], py[t], pz[t], pidx);
-                    }
+                for (int t = 0; t < 4; ++t) {
+                    px[t] = py[t] = pz[t] = 0.0;
+                    uint32_t pidx;
+                    if ((uint32_t)(b + t) < cnt) load_point(A.pts, it.x + (uint32_t)(b + t), px[t], py[t], pz[t], pidx);
+                }
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const double v = sumsq3(dsub(px[t], s.qx), dsub(py[t], s.qy), dsub(pz[t], s.qz));
-                        if ((uint32_t)(b + t) < cnt && v <= s.bound) {
-                            if (v < best) {
-                                second = best;
-                                best = v;
-                                bpos = it.x + (uint32_t)(b + t);
-                            } else if (v < second) {
-                                second = v;
-                            }
+                for (int t = 0; t < 4; ++t) {
+                    const double v = sumsq3(dsub(px[t], s.qx), dsub(py[t], s.qy), dsub(pz[t], s.qz));
+                    if ((uint32_t)(b + t) < cnt && v <= s.bound) {
+                        if (v < best) {
+                            second = best;
+                            best = v;
+                            bpos = it.x + (uint32_t)(b + t);
+                        } else if (v < second) {
+                            second = v;
                         }
                     }
                 }
             }
-            if (has) {
-                rbest[j] = best;
-                queue[j] = make_uint2(bpos, (bpos != NONE && !(second > dmul(best, 1.0 + 9.094947017729282e-13))) ? 1u : 0u);
-            }
         }
-        __syncwarp();
-        // merge the own items; unique minimum with margin 2^-40 => the reference's answer
-        if (go) {
-            double gb = ICPB_INF, gs = ICPB_INF;
-            uint32_t gpos = NONE, gtie = 0u;
-            for (uint32_t k = off_begin; k < off_end; ++k) {
-                const double b = rbest[k];
-                const uint2 r = queue[k];
-                if (b < gb) {
-                    gs = gb;
-                    gb = b;
-                    gpos = r.x;
-                    gtie = r.y;
-                } else if (b < gs) {
-                    gs = b;
-                }
-            }
-            if (gpos != NONE && gtie == 0u && gs > dmul(gb, 1.0 + 9.094947017729282e-13)) {
-                settled = true;
-                A.pos_out[i] = gpos;
-                A.dist_out[i] = dsqrt(gb);  // computeDistance (icpengine.cpp:68-74): sqrt of the same sum of squares
-            }
-            waiting = false;
+        if (has) {
+            rbest[j] = best;
+            queue[j] = make_uint2(bpos, (bpos != NONE && !(second > dmul(best, 1.0 + 9.094947017729282e-13))) ? 1u : 0u);
         }
-        __syncwarp();  // the next round refills the queue
     }
-    const uint32_t total = 0u;  // (counter below)
+    __syncwarp();
+
+    // ---- C. merge the own items; unique minimum with margin 2^-40 => the reference's answer ----
+    bool settled = false;
+    if (elig) {
+        double gb = ICPB_INF, gs = ICPB_INF;
+        uint32_t gpos = NONE, gtie = 0u;
+        for (uint32_t k = off_begin; k < off_end; ++k) {
+            const double b = rbest[k];
+            const uint2 r = queue[k];
+            if (b < gb) {
+                gs = gb;
+                gb = b;
+                gpos = r.x;
+                gtie = r.y;
+            } else if (b < gs) {
+                gs = b;
+            }
+        }
+        if (gpos != NONE && gtie == 0u && gs > dmul(gb, 1.0 + 9.094947017729282e-13)) {
+            settled = true;
+            A.pos_out[i] = gpos;
+            A.dist_out[i] = dsqrt(gb);  // computeDistance (icpengine.cpp:68-74): sqrt of the same sum of squares
+        }
+    }
     const unsigned pend = __ballot_sync(FULL, active && !settled);
     if (pend) {
         unsigned int at = 0;
@@ -253,7 +236,7 @@ __global__ void __launch_bounds__(GW_THREADS, GWL_MINBLOCKS) nn_group_lean_kerne
             if (ok) atomicAdd(&A.counters[0], (unsigned long long)__popc(ok));
             if (pend) atomicAdd(&A.counters[2], (unsigned long long)__popc(pend));
             atomicAdd(&A.counters[3], (unsigned long long)cand);
-            atomicAdd(&A.counters[4], (unsigned long long)total);  // (items are no longer counted)
+            atomicAdd(&A.counters[4], (unsigned long long)total);
         }
     }
 }
