@@ -376,13 +376,14 @@ static int run_loop(Ctx* c, int64_t n_global, icp_result* out, const volatile in
         if (iter == 0) out->ms_nn_first = nn_ms;
         out->loop_iterations = iter + 1;
         if (debug_iter) {  // profiling aid: counters and work-list lengths of this iteration
-            unsigned long long w[8];
+            unsigned long long w[16];
             unsigned int wc[16];
             cudaMemcpy(w, c->d_counters, sizeof w, cudaMemcpyDeviceToHost);
             cudaMemcpy(wc, c->d_work_count, sizeof wc, cudaMemcpyDeviceToHost);
             for (int k = 2; k < 10; ++k) wc[0] += wc[k];  // the balanced walk keeps one list per chunk of queries
-            fprintf(stderr, "[icp_b200] iter %d nn %.3f ms: settled=%llu literal=%llu slow=%llu candidates=%llu items=%llu kept=%llu | list1=%u list2=%u\n",
-                    iter, nn_ms, w[0], w[1], w[2], w[3], w[4], w[5], wc[0], wc[1]);
+            fprintf(stderr, "[icp_b200] iter %d nn %.3f ms: settled=%llu literal=%llu slow=%llu candidates=%llu items=%llu kept=%llu | list1=%u list2=%u"
+                            " | left the walk: no seed %llu, wide ball %llu, crowded cell %llu, queue overflow %llu, no unique minimum %llu\n",
+                    iter, nn_ms, w[0], w[1], w[2], w[3], w[4], w[5], wc[0], wc[1], w[9], w[10], w[11], w[12], w[13]);
             cudaMemset(c->d_counters, 0, sizeof w);
         }
         prev_rmse = rec.rmse;
@@ -622,8 +623,8 @@ int icp_create(icp_handle* out, int device_id) {
     for (auto& e : c->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaMalloc(&c->d_state, sizeof(LoopState)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
-    if (cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
-    cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long));
+    if (cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
+    cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long));
     if (cudaMalloc(&c->d_work_count, 16 * sizeof(unsigned int)) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     if (cudaHostAlloc(&c->h_rec, Ctx::REC_RING * sizeof(IterRecord), cudaHostAllocMapped) != cudaSuccess) { delete c; return ICP_CUDA_ERROR; }
     for (auto& e : c->ev_it)

@@ -48,6 +48,12 @@ __global__ void __launch_bounds__(GW_THREADS) nn_group_lean_kernel(const NNArgs 
     // ---- A. own query ----
     double qx = 0.0, qy = 0.0, qz = 0.0, bound = 0.0;
     bool elig = false;
+#ifdef ICPB_WHY
+    int why = 0;  // profiling build only (make EXTRA=-DICPB_WHY): 1 no seed, 2 ball over more than two cells along an axis, 3 crowded cell, 4 queue overflow, 5 no unique minimum
+#define ICPB_WHY_SET(v) why = (v)
+#else
+#define ICPB_WHY_SET(v)
+#endif
     uint32_t ept[8], ecnt[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) ept[c] = ecnt[c] = 0u;
@@ -118,8 +124,15 @@ __global__ void __launch_bounds__(GW_THREADS) nn_group_lean_kernel(const NNArgs 
                         ecnt[c] = en[c].y & 0xFFFFFFu;
                     }
                 }
-                if (crowded) elig = false;
+                if (crowded) {
+                    elig = false;
+                    ICPB_WHY_SET(3);
+                }
+            } else {
+                ICPB_WHY_SET(2);
             }
+        } else {
+            ICPB_WHY_SET(1);
         }
     }
 
@@ -137,7 +150,10 @@ __global__ void __launch_bounds__(GW_THREADS) nn_group_lean_kernel(const NNArgs 
     }
     const uint32_t off_begin = off_end - nsub;
     const bool fits = off_end <= (uint32_t)GW_QCAP;
-    if (!fits) elig = false;
+    if (!fits) {
+        if (elig) ICPB_WHY_SET(4);
+        elig = false;
+    }
     const uint32_t total = __reduce_max_sync(FULL, fits ? off_end : 0u);
     if (elig) {
         uint32_t o = off_begin;
@@ -238,6 +254,14 @@ __global__ void __launch_bounds__(GW_THREADS) nn_group_lean_kernel(const NNArgs 
             atomicAdd(&A.counters[3], (unsigned long long)cand);
             atomicAdd(&A.counters[4], (unsigned long long)total);
         }
+#ifdef ICPB_WHY
+        if (active && !settled && why == 0) why = 5;
+#pragma unroll
+        for (int r = 1; r <= 5; ++r) {
+            const unsigned m = __ballot_sync(FULL, active && !settled && why == r);
+            if (lane == 0 && m) atomicAdd(&A.counters[8 + r], (unsigned long long)__popc(m));
+        }
+#endif
     }
 }
 
