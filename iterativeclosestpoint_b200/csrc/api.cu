@@ -507,7 +507,9 @@ static int register_impl(Ctx* c, double* src_xyz, int64_t n_src, int64_t n_src_g
                          icp_result* out, const volatile int* stop_flag, const icp_las_points* src_las = nullptr,
                          const icp_las_points* tgt_las = nullptr) {
     init_result(out);
-    if ((!src_xyz && !src_las) || (!tgt_xyz && !tgt_las) || n_src_global <= 0 || n_tgt <= 0) {  // icpengine.cpp:26-34
+    // (an EMPTY shard of a sharded source is a supported case: the rank still takes part in every collective)
+    const bool no_source = c->n_ranks > 1 ? (n_src < 0 || (n_src > 0 && !src_xyz)) : ((!src_xyz && !src_las) || n_src <= 0);
+    if (no_source || (!tgt_xyz && !tgt_las) || n_src_global <= 0 || n_tgt <= 0) {  // icpengine.cpp:26-34
         out->status = ICP_EMPTY_INPUT;
         return ICP_EMPTY_INPUT;
     }
@@ -1082,9 +1084,9 @@ int icp_apply_transform(icp_handle h, const double* T16, double* xyz, int64_t n)
 int icp_source_upload(icp_handle h, const double* src_xyz, int64_t n_src) {
     Ctx* c = (Ctx*)h;
     if (!c) return ICP_INVALID_ARGUMENT;
-    if (!src_xyz || n_src <= 0) return ICP_EMPTY_INPUT;
+    if (c->n_ranks > 1 ? (n_src < 0 || (n_src > 0 && !src_xyz)) : (!src_xyz || n_src <= 0)) return ICP_EMPTY_INPUT;  // (empty shards allowed)
     ICPB_CUDA(c, cudaSetDevice(c->device));
-    ICPB_TRY(upload(c, c->scratch_src, src_xyz, n_src));
+    if (n_src > 0) ICPB_TRY(upload(c, c->scratch_src, src_xyz, n_src));
     c->src_identity_perm = false;
     ICPB_TRY(source_from_shard(c, (const double*)c->scratch_src.p, n_src));  // (collective on a sharded handle)
     ICPB_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -16,6 +16,9 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
 src, tgt = sharding.shared_pair(m, 3, "primary", lr, world, dist.barrier)
+# ICP_CHECK_SRC=k: only the first k source points against the m-point target (k < world leaves ranks with EMPTY shards)
+n_pair = m
+m = int(os.environ.get("ICP_CHECK_SRC", m)); src = src[:m]
 lo, hi = sharding.shard_range(m, rank, world)
 max_it = int(os.environ.get("ICP_CHECK_ITERS", "30"))
 with_oracle = os.environ.get("ICP_CHECK_ORACLE", "0") == "1"
@@ -40,7 +43,7 @@ for a, b in zip(res.iterationHistory, ref.iterationHistory):
     check(a.validPoints == b.validPoints, f"valid {a.validPoints} vs {b.validPoints} at {a.iteration}")
     dev["rmse_rel"] = max(dev["rmse_rel"], abs(a.rmse - b.rmse) / b.rmse)
     dev["T_rel"] = max(dev["T_rel"], float(np.max(np.abs(a.transform - b.transform)) / max(1.0, np.max(np.abs(b.transform)))))
-dev["shard_rel"] = float(np.max(np.abs(shard - full[lo:hi])) / np.max(np.abs(full)))
+if hi > lo: dev["shard_rel"] = float(np.max(np.abs(shard - full[lo:hi])) / np.max(np.abs(full)))
 check(dev["rmse_rel"] <= 1e-9, f"rmse rel {dev['rmse_rel']:.3e}")
 check(dev["T_rel"] <= 1e-9, f"T rel {dev['T_rel']:.3e}")
 check(dev["shard_rel"] <= 1e-9, f"moved shard rel {dev['shard_rel']:.3e}")
@@ -56,6 +59,7 @@ if with_oracle and rank == 0:
     from oracle.binding import Oracle
     orc = Oracle(); otree = orc.octree(tgt)
     rs = np.random.default_rng(44).permutation(hi - lo)
+    assert hi - lo >= 60000, "the oracle sample needs 60000 points on rank 0"
     h1.octree_build(tgt, 10, 20)
     bad = 0
     for sample, cloud in ((rs[:30000], np.ascontiguousarray(src[lo:hi])), (rs[30000:60000], shard)):
@@ -66,7 +70,7 @@ if with_oracle and rank == 0:
     oracle_note = f"NN indices of 2 x 30000 sampled queries (start pose, final pose) vs the oracle: {bad} mismatches"
 # the resident entry points take the same road (redistribution over NVLink, return on write-back)
 h.source_upload(np.ascontiguousarray(src[lo:hi]))
-back = np.zeros((hi - lo, 3))
+back = np.ascontiguousarray(src[lo:hi]).copy()  # (a run that ends without a write-back leaves it as it was, like icp_register_sharded)
 res2 = h.register_resident(m, source_out=back)
 check(res2.totalIterations == ref.totalIterations and np.array_equal(res2.cumulativeT, res.cumulativeT), "resident run differs from icp_register_sharded")
 check(np.array_equal(back, shard), "resident write-back differs")
@@ -82,14 +86,17 @@ shard4 = np.ascontiguousarray(src[lo:hi]).copy()
 res4 = h.register_sharded(shard4, m, tgt)
 check(np.array_equal(res4.cumulativeT, res.cumulativeT) and np.array_equal(shard4, shard), "run after a cancelled run differs")
 flag = torch.tensor([1 if ok else 0], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+all_notes = [None] * world; dist.all_gather_object(all_notes, notes[:5])
+notes = [f"rank {r}: {n}" for r, ns in enumerate(all_notes) for n in ns]
 if rank == 0:
     line = {"sharded_parity_ok": bool(flag.item()), "world": world, "points": m, "iterations": res.totalIterations,
             "final_rmse": res.finalRMSE, "max_deviation_vs_1gpu": dev,
             "checks": ["iterations / inlier counts equal the 1-GPU run", "transforms, rmse, moved shards <= 1e-9 vs 1-GPU (found: max_deviation_vs_1gpu)", "ranks bit-identical", "resident path == host path", "stop on one rank cancels all ranks",
             "run after a cancelled run unharmed"], "timings_ms": {k: round(float(v), 3) for k, v in res.timings_ms.items()},
-            "timings_ms_second_run": {k: round(float(v), 3) for k, v in res4.timings_ms.items()}, "oracle": oracle_note, "notes": notes[:5]}
+            "timings_ms_second_run": {k: round(float(v), 3) for k, v in res4.timings_ms.items()}, "oracle": oracle_note, "notes": notes[:16]}
     print(json.dumps(line), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
+    line["target_points"] = n_pair
     with open(f"gpurun_out/sharded_check_{world}gpu_{m}.json", "w") as f:
         json.dump(line, f)
 dist.barrier(); dist.destroy_process_group(); h.close(); h1.close()
