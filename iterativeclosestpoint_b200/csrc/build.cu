@@ -51,9 +51,6 @@ void devbuf_free(DevBuf& b) {
 // ------------------------------------------------------------------------------------------------
 // exclusive scan of uint32 (three kernels; sizes here are at most a few 10^7)
 // ------------------------------------------------------------------------------------------------
-constexpr int SCAN_THREADS = 512;
-constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem_warp, uint32_t* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -81,73 +78,6 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
     *total = smem_warp[32];
     __syncthreads();
     return res;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const uint32_t* __restrict__ in,
-                                                                  uint32_t* __restrict__ out, int64_t n,
-                                                                  uint32_t* __restrict__ tile_sums) {
-    __shared__ uint32_t sw[33];
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-    uint32_t v[SCAN_ITEMS];
-    uint32_t sum = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        v[k] = (base + k < n) ? in[base + k] : 0u;
-        sum += v[k];
-    }
-    uint32_t total;
-    uint32_t off = block_exclusive_scan(sum, sw, &total);
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        if (base + k < n) out[base + k] = off;
-        off += v[k];
-    }
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-
-// single block: exclusive scan of the tile sums in place; writes the grand total
-__global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t* __restrict__ sums, int n, uint32_t* __restrict__ total_out) {
-    __shared__ uint32_t sw[33];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        int i = base + threadIdx.x;
-        uint32_t v = (i < n) ? sums[i] : 0u;
-        uint32_t tot;
-        uint32_t off = block_exclusive_scan(v, sw, &tot);
-        uint32_t c0 = carry;
-        if (i < n) sums[i] = c0 + off;
-        __syncthreads();
-        if (threadIdx.x == 0) carry = c0 + tot;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && total_out) *total_out = carry;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t* __restrict__ out, int64_t n,
-                                                                const uint32_t* __restrict__ tile_offsets) {
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-    const uint32_t off = tile_offsets[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k)
-        if (base + k < n) out[base + k] += off;
-}
-
-int exclusive_scan_u32(Ctx* c, const uint32_t* d_in, uint32_t* d_out, int64_t n, uint32_t* d_total) {
-    if (n <= 0) {
-        if (d_total) ICPB_CUDA(c, cudaMemsetAsync(d_total, 0, sizeof(uint32_t), c->stream));
-        return ICP_OK;
-    }
-    const int tiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
-    ICPB_TRY(devbuf_reserve(c, c->scratch3, (size_t)tiles * sizeof(uint32_t)));
-    uint32_t* sums = (uint32_t*)c->scratch3.p;
-    scan_tiles_kernel<<<tiles, SCAN_THREADS, 0, c->stream>>>(d_in, d_out, n, sums);
-    scan_sums_kernel<<<1, 1024, 0, c->stream>>>(sums, tiles, d_total);
-    scan_add_kernel<<<tiles, SCAN_THREADS, 0, c->stream>>>(d_out, n, sums);
-    c->launches += 3;
-    ICPB_CUDA(c, cudaGetLastError());
-    return ICP_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -222,6 +152,7 @@ __global__ void cube_root_kernel(double* __restrict__ root) {
 // A 64-bit word holds 21 levels; a deeper tree (the reference accepts octreeMaxDepth up to 50, settingspage.cpp:76) takes
 // ceil(max_depth / 21) words per point: word w of point i at keys[w * n + i], most significant word first.
 constexpr int KEY_LEVELS = 21;
+constexpr int KEY_DEPTH_FIRST = 16;  // levels of octant keys a build takes first (build_tree)
 
 __global__ void __launch_bounds__(256) morton_keys_kernel(const double* __restrict__ xyz, int64_t n,
                                                           const double* __restrict__ root, int max_depth,
@@ -269,67 +200,127 @@ constexpr int RS_ROUNDS = 16;                            // elements per thread
 constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;          // 4096 elements per block
 constexpr int RS_CHUNK = 32 * RS_ROUNDS;                 // per warp
 
-__device__ __forceinline__ void warp_digit_hist(const uint64_t* __restrict__ keys, int64_t n, int64_t chunk_base,
-                                                int shift, uint32_t* hist /* smem [256] of this warp */) {
-    const int lane = threadIdx.x & 31;
-#pragma unroll 4
-    for (int r = 0; r < RS_ROUNDS; ++r) {
-        const int64_t i = chunk_base + (int64_t)r * 32 + lane;
-        const bool ok = i < n;
-        const uint32_t d = ok ? (uint32_t)((keys[i] >> shift) & 0xFF) : 0x100u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        if (ok && (peers & ((1u << lane) - 1u)) == 0) hist[d] += __popc(peers);
-        __syncwarp();
+// One pass = ONE kernel (chained scan with decoupled look-back): the digit histograms of ALL passes are taken up front in a
+// single read of the keys (they do not depend on the order), so a pass only has to find, for each of its tiles, how many
+// keys of every digit lie in the tiles before it.  A tile publishes its own digit counts at once (AGGREGATE), then walks back
+// over its predecessors' words until it meets one that already holds an inclusive PREFIX, and publishes its own prefix.
+// Tiles are handed out by an atomic ticket, so every predecessor of a waiting tile is running or done: no deadlock.
+constexpr uint64_t OS_AGG = 1ull << 62, OS_INCL = 2ull << 62, OS_VAL = OS_AGG - 1;
+constexpr int OS_MAX_PASSES = 8;
+
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ghist[p][d] += number of keys whose digit of pass p is d.  A thread keeps a run (digit, count) per pass in registers and
+// only touches shared memory when the digit changes: clouds in scan order have long runs in the upper digits, which would
+// otherwise serialise the shared-memory atomics of a warp on one address.
+template <int P>
+__global__ void __launch_bounds__(256) radix_hist_all_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t h[P][256];
+    for (int k = threadIdx.x; k < P * 256; k += 256) (&h[0][0])[k] = 0;
+    __syncthreads();
+    uint32_t cur[P], cnt[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) cur[p] = cnt[p] = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const uint64_t key = __ldg(keys + i);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const uint32_t d = (uint32_t)(key >> (8 * p)) & 0xFFu;
+            if (d == cur[p]) {
+                ++cnt[p];
+            } else {
+                if (cnt[p]) atomicAdd(&h[p][cur[p]], cnt[p]);
+                cur[p] = d;
+                cnt[p] = 1;
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+        if (cnt[p]) atomicAdd(&h[p][cur[p]], cnt[p]);
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const uint32_t v = h[p][threadIdx.x];
+        if (v) atomicAdd(&ghist[p * 256 + threadIdx.x], v);
     }
 }
 
-// hist_out is digit-major: hist_out[d * n_blocks + block]
-__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift,
-                                                                uint32_t* __restrict__ hist_out, int n_blocks) {
-    __shared__ uint32_t wh[RS_WARPS][256];
-    for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&wh[0][0])[k] = 0;
-    __syncthreads();
-    const int warp = threadIdx.x >> 5;
-    const int64_t chunk_base = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * RS_CHUNK;
-    warp_digit_hist(keys, n, chunk_base, shift, wh[warp]);
-    __syncthreads();
-    uint32_t s = 0;
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) s += wh[w][threadIdx.x];
-    hist_out[(int64_t)threadIdx.x * n_blocks + blockIdx.x] = s;
+// block p: gstart[p][d] = number of keys whose digit of pass p is smaller than d
+__global__ void __launch_bounds__(256) radix_digit_scan_kernel(const uint32_t* __restrict__ ghist, uint32_t* __restrict__ gstart) {
+    __shared__ uint32_t sw[33];
+    const uint32_t v = ghist[blockIdx.x * 256 + threadIdx.x];
+    uint32_t total;
+    gstart[blockIdx.x * 256 + threadIdx.x] = block_exclusive_scan(v, sw, &total);
 }
 
-// Scatter of one pass, staged through shared memory: the block first puts its tile in digit order LOCALLY (same ranking as
-// before: per-warp running offsets, __match_any_sync inside a round, so equal digits keep their input order), then copies the
-// staged tile out -- neighbouring threads now write neighbouring addresses of the same digit's run (16 elements per digit and
-// tile on average = whole 128-byte lines) instead of 32 different runs per warp store.
-constexpr size_t RS_SCATTER_SMEM = (size_t)RS_TILE * (sizeof(uint64_t) + sizeof(uint32_t)) + (RS_WARPS * 256 + 512 + 8) * sizeof(uint32_t);
+// The scatter of one pass.  Each warp owns a contiguous chunk of the tile and walks it in rounds of 32 consecutive keys (kept
+// in registers), ranking equal digits by __match_any_sync, so ranks follow input order (stability).  The tile is first put in
+// digit order in shared memory, then copied out: neighbouring threads write neighbouring addresses of the same digit's run.
+constexpr size_t RS_SCATTER_SMEM = (size_t)RS_TILE * (sizeof(uint64_t) + sizeof(uint32_t)) + (RS_WARPS * 256 + 512 + 16) * sizeof(uint32_t);
 
-__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint64_t* __restrict__ keys_in,
-                                                                   const uint32_t* __restrict__ vals_in, int64_t n,
-                                                                   int shift, const uint32_t* __restrict__ hist_scan,
-                                                                   int n_blocks, uint64_t* __restrict__ keys_out,
-                                                                   uint32_t* __restrict__ vals_out) {
+__global__ void __launch_bounds__(RS_THREADS, 3) radix_onesweep_kernel(const uint64_t* __restrict__ keys_in,
+                                                                       const uint32_t* __restrict__ vals_in, int64_t n, int shift,
+                                                                       const uint32_t* __restrict__ gstart /* [256] of this pass */,
+                                                                       uint64_t* __restrict__ status /* [tiles][256], zeroed */,
+                                                                       uint32_t* __restrict__ ticket /* zeroed */,
+                                                                       uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     uint64_t* skeys = reinterpret_cast<uint64_t*>(rs_smem);              // [RS_TILE]
     uint32_t* svals = reinterpret_cast<uint32_t*>(skeys + RS_TILE);      // [RS_TILE]
-    uint32_t (*wh)[256] = reinterpret_cast<uint32_t (*)[256]>(svals + RS_TILE);  // [RS_WARPS][256] per-warp histogram, then offsets
+    uint32_t (*wh)[256] = reinterpret_cast<uint32_t (*)[256]>(svals + RS_TILE);  // [RS_WARPS][256] per-warp counts, then offsets
     uint32_t* dstart = &wh[0][0] + RS_WARPS * 256;                       // [256] start of digit d inside the staged tile
-    uint32_t* gbase = dstart + 256;                                      // [256] start of this block's digit-d run in the output
+    uint32_t* gbase = dstart + 256;                                      // [256] start of this tile's digit-d run in the output
     uint32_t* wtot = gbase + 256;                                        // [8]
+    uint32_t* s_tile = wtot + 8;
+    if (threadIdx.x == 0) *s_tile = atomicAdd(ticket, 1u);
     for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&wh[0][0])[k] = 0;
     __syncthreads();
+    const uint32_t tile = *s_tile;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t block_base = (int64_t)blockIdx.x * RS_TILE;
+    const int64_t block_base = (int64_t)tile * RS_TILE;
     const int64_t chunk_base = block_base + (int64_t)warp * RS_CHUNK;
-    warp_digit_hist(keys_in, n, chunk_base, shift, wh[warp]);
+    uint64_t key[RS_ROUNDS];
+    uint32_t rank2[RS_ROUNDS / 2];  // position among the keys of the same digit in this warp's chunk (< 512): two per word
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS / 2; ++r) rank2[r] = 0;
+    {
+        uint32_t* hist = wh[warp];
+        const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int r = 0; r < RS_ROUNDS; ++r) {
+            const int64_t i = chunk_base + (int64_t)r * 32 + lane;
+            const bool ok = i < n;
+            key[r] = ok ? keys_in[i] : ~0ull;
+            const uint32_t d = ok ? (uint32_t)((key[r] >> shift) & 0xFF) : 0x100u;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t before = __popc(peers & lt);
+            uint32_t old = 0;
+            if (ok && before == 0) {
+                old = hist[d];
+                hist[d] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+            rank2[r >> 1] |= (old + before) << (16 * (r & 1));
+            __syncwarp();
+        }
+    }
     __syncthreads();
     {
-        // thread d: this block's count of digit d, exclusive scan over the digits (staging order), offsets per warp
+        // thread d: this tile's count of digit d; publish it; scan over the digits (staging order) and per-warp offsets
         const int d = threadIdx.x;
         uint32_t cnt = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) cnt += wh[w][d];
+        uint64_t* my = status + (size_t)tile * 256 + d;
+        st_relaxed_u64(my, (uint64_t)cnt | (tile == 0 ? OS_INCL : OS_AGG));
         uint32_t incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -342,68 +333,98 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint64_
         for (int w = 0; w < warp; ++w) before_warps += wtot[w];
         uint32_t run = before_warps + incl - cnt;
         dstart[d] = run;
-        gbase[d] = hist_scan[(int64_t)d * n_blocks + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
             const uint32_t c = wh[w][d];
             wh[w][d] = run;
             run += c;
         }
+        // look back over the tiles before this one
+        uint64_t excl = 0;
+        if (tile > 0) {
+            const uint64_t* look = my - 256;
+            for (;;) {
+                uint64_t v;
+                do {
+                    v = ld_relaxed_u64(look);
+                } while ((v >> 62) == 0);
+                excl += v & OS_VAL;
+                if ((v >> 62) == 2) break;
+                look -= 256;
+            }
+            st_relaxed_u64(my, (excl + cnt) | OS_INCL);
+        }
+        gbase[d] = gstart[d] + (uint32_t)excl;
     }
     __syncthreads();
-    uint32_t* off = wh[warp];
-#pragma unroll 4
-    for (int r = 0; r < RS_ROUNDS; ++r) {
-        const int64_t i = chunk_base + (int64_t)r * 32 + lane;
-        const bool ok = i < n;
-        uint64_t key = 0;
-        uint32_t val = 0;
-        if (ok) {
-            key = keys_in[i];
-            val = vals_in[i];
+    {
+        const uint32_t* off = wh[warp];
+#pragma unroll
+        for (int r = 0; r < RS_ROUNDS; ++r) {
+            const int64_t i = chunk_base + (int64_t)r * 32 + lane;
+            if (i < n) {
+                const uint32_t d = (uint32_t)((key[r] >> shift) & 0xFF);
+                const uint32_t dst = off[d] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xFFFFu);  // position inside the staged tile
+                skeys[dst] = key[r];
+                svals[dst] = vals_in[i];
+            }
         }
-        const uint32_t d = ok ? (uint32_t)((key >> shift) & 0xFF) : 0x100u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const uint32_t before = __popc(peers & ((1u << lane) - 1u));
-        uint32_t base = 0;
-        if (ok) base = off[d];
-        __syncwarp();
-        if (ok) {
-            const uint32_t dst = base + before;  // position inside the staged tile
-            skeys[dst] = key;
-            svals[dst] = val;
-            if (before == 0) off[d] = base + __popc(peers);
-        }
-        __syncwarp();
     }
     __syncthreads();
     const int count = (int)min((int64_t)RS_TILE, n - block_base);
     for (int j = threadIdx.x; j < count; j += RS_THREADS) {
-        const uint64_t key = skeys[j];
-        const uint32_t d = (uint32_t)((key >> shift) & 0xFF);
+        const uint64_t k = skeys[j];
+        const uint32_t d = (uint32_t)((k >> shift) & 0xFF);
         const uint32_t dst = gbase[d] + ((uint32_t)j - dstart[d]);
-        keys_out[dst] = key;
+        keys_out[dst] = k;
         vals_out[dst] = svals[j];
     }
 }
 
+template <int P>
+static void hist_all_launch(Ctx* c, const uint64_t* keys, int64_t n, uint32_t* ghist) {
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 8);
+    radix_hist_all_kernel<P><<<blocks, 256, 0, c->stream>>>(keys, n, ghist);
+}
+
 static int radix_sort_pairs(Ctx* c, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& vals, uint32_t*& vals_alt,
                             int64_t n, int key_bits) {
-    const int n_blocks = (int)((n + RS_TILE - 1) / RS_TILE);
-    const int64_t hist_n = (int64_t)256 * n_blocks;
+    if (n <= 0 || key_bits <= 0) return ICP_OK;
+    const int n_pass = (key_bits + 7) / 8;
+    if (n_pass > OS_MAX_PASSES) {
+        c->err = "radix sort: more than 64 key bits";
+        return ICP_INVALID_ARGUMENT;
+    }
+    const int64_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
     if (!c->rs_smem_opt_in) {  // more than 48 KB of dynamic shared memory: opt in once per handle (= per device context)
-        ICPB_CUDA(c, cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM));
+        ICPB_CUDA(c, cudaFuncSetAttribute(radix_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM));
         c->rs_smem_opt_in = true;
     }
-    ICPB_TRY(devbuf_reserve(c, c->scratch2, (size_t)hist_n * sizeof(uint32_t) * 2));
-    uint32_t* hist = (uint32_t*)c->scratch2.p;
-    uint32_t* hist_scan = hist + hist_n;
-    for (int shift = 0; shift < key_bits; shift += 8) {
-        radix_hist_kernel<<<n_blocks, RS_THREADS, 0, c->stream>>>(keys, n, shift, hist, n_blocks);
-        c->launches++;
-        ICPB_TRY(exclusive_scan_u32(c, hist, hist_scan, hist_n, nullptr));
-        radix_scatter_kernel<<<n_blocks, RS_THREADS, RS_SCATTER_SMEM, c->stream>>>(keys, vals, n, shift, hist_scan, n_blocks,
-                                                                                   keys_alt, vals_alt);
+    // scratch: ghist[8][256] | gstart[8][256] | ticket (64 B) | status[n_tiles][256]
+    const size_t head = (size_t)2 * OS_MAX_PASSES * 256 * sizeof(uint32_t);
+    const size_t status_bytes = 64 + (size_t)n_tiles * 256 * sizeof(uint64_t);
+    ICPB_TRY(devbuf_reserve(c, c->scratch2, head + status_bytes));
+    uint32_t* ghist = (uint32_t*)c->scratch2.p;
+    uint32_t* gstart = ghist + OS_MAX_PASSES * 256;
+    uint32_t* ticket = (uint32_t*)((char*)c->scratch2.p + head);
+    uint64_t* status = (uint64_t*)((char*)ticket + 64);
+    ICPB_CUDA(c, cudaMemsetAsync(ghist, 0, OS_MAX_PASSES * 256 * sizeof(uint32_t), c->stream));
+    switch (n_pass) {
+        case 1: hist_all_launch<1>(c, keys, n, ghist); break;
+        case 2: hist_all_launch<2>(c, keys, n, ghist); break;
+        case 3: hist_all_launch<3>(c, keys, n, ghist); break;
+        case 4: hist_all_launch<4>(c, keys, n, ghist); break;
+        case 5: hist_all_launch<5>(c, keys, n, ghist); break;
+        case 6: hist_all_launch<6>(c, keys, n, ghist); break;
+        case 7: hist_all_launch<7>(c, keys, n, ghist); break;
+        default: hist_all_launch<8>(c, keys, n, ghist); break;
+    }
+    radix_digit_scan_kernel<<<n_pass, 256, 0, c->stream>>>(ghist, gstart);
+    c->launches += 2;
+    for (int p = 0; p < n_pass; ++p) {
+        ICPB_CUDA(c, cudaMemsetAsync(ticket, 0, status_bytes, c->stream));
+        radix_onesweep_kernel<<<(unsigned)n_tiles, RS_THREADS, RS_SCATTER_SMEM, c->stream>>>(keys, vals, n, 8 * p, gstart + p * 256, status,
+                                                                                             ticket, keys_alt, vals_alt);
         c->launches++;
         std::swap(keys, keys_alt);
         std::swap(vals, vals_alt);
@@ -452,77 +473,221 @@ __device__ __forceinline__ uint32_t lower_bound_octant(const uint64_t* __restric
     return lo;
 }
 
-// counts[i] = number of non-empty octants of level node i (0 for leaves)
-__global__ void __launch_bounds__(128) node_count_kernel(const Node* __restrict__ nodes, uint32_t first, uint32_t count,
-                                                         const uint64_t* __restrict__ keys, int level, int max_pts,
-                                                         int max_depth, int shift, uint32_t* __restrict__ counts) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    const Node& nd = nodes[first + t];
-    uint32_t nchild = 0;
-    if (!(nd.npts <= (uint32_t)max_pts || level >= max_depth)) {  // octree.cpp:88
-        uint32_t b = nd.pt0;
-        const uint32_t end = nd.pt0 + nd.npts;
-        for (uint32_t oct = 1; oct <= 8; ++oct) {
-            uint32_t e = (oct == 8) ? end : lower_bound_octant(keys, b, end, shift, oct);
-            nchild += (e > b) ? 1u : 0u;
-            b = e;
-        }
-    }
-    counts[t] = nchild;
+// All levels in ONE cooperative launch (every block resident, a grid barrier between levels).  Eight lanes per node: lane
+// `oct` finds where octant `oct` starts in the node's sorted range, its neighbour's start is where it ends.  A block takes
+// tiles of LV_TILE nodes of the level in increasing order; the first-child index of a node is the number of children of all
+// nodes before it, found without a second pass: a tile publishes its own child count at once and looks back over the
+// earlier tiles' words (chained scan, as in the sort above; a block never waits for a later tile, so it cannot deadlock).
+// The node numbering is the breadth-first one a count / scan / emit sequence per level gives.
+constexpr int LV_THREADS = 256, LV_ROUNDS = 4, LV_TILE = 32 * LV_ROUNDS;
+constexpr uint32_t LV_FLAG_CAPACITY = 1, LV_FLAG_DEEPER = 2;
+
+struct LevelState {  // zeroed before the launch
+    uint32_t level_total[66];  // children emitted from level L (written by that level's last tile)
+    uint32_t level_flags[66];  // flags raised while level L was processed: what the blocks decide on after that level's barrier
+                               // (a block still reading after barrier L must not see what a faster block raises in L + 1)
+    uint32_t n_leaves;
+    uint32_t flags;            // LV_FLAG_CAPACITY: the node table is too small; LV_FLAG_DEEPER: a node must split below key_depth
+    uint32_t needed;           // node slots wanted so far
+    uint32_t depth, n_nodes;   // the result
+    uint32_t barrier;
+};
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
-__global__ void __launch_bounds__(128) node_emit_kernel(Node* __restrict__ nodes, uint32_t first, uint32_t count,
-                                                        const uint64_t* __restrict__ keys, int level, int max_pts,
-                                                        int max_depth, int shift, const uint32_t* __restrict__ child_off,
-                                                        uint32_t next_first, uint32_t* __restrict__ leaf_counter,
-                                                        uint32_t* __restrict__ parent, uint64_t* __restrict__ cell) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    Node nd = nodes[first + t];
-    if (nd.npts <= (uint32_t)max_pts || level >= max_depth) {
-        nodes[first + t].meta = ((uint32_t)level << 8);  // leaf: empty child mask
-        nodes[first + t].child0 = 0;
-        atomicAdd(leaf_counter, 1u);
-        return;
-    }
-    double mid[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) mid[a] = dmul(dadd(nd.lo[a], nd.hi[a]), 0.5);  // octree.cpp:97-99
-    uint32_t b = nd.pt0;
-    const uint32_t end = nd.pt0 + nd.npts;
-    uint32_t mask = 0, k = 0;
-    const uint32_t c0 = next_first + child_off[t];
-    for (uint32_t oct = 0; oct < 8; ++oct) {
-        const uint32_t e = (oct == 7) ? end : lower_bound_octant(keys, b, end, shift, oct + 1);
-        if (e > b) {
-            Node ch;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {  // octree.cpp:115-120
-                const bool up = (oct >> a) & 1u;
-                ch.lo[a] = up ? mid[a] : nd.lo[a];
-                ch.hi[a] = up ? nd.hi[a] : mid[a];
-            }
-            ch.child0 = 0;
-            ch.pt0 = b;
-            ch.npts = e - b;
-            ch.meta = ((uint32_t)(level + 1) << 8);
-            nodes[c0 + k] = ch;
-            parent[c0 + k] = first + t;
-            if (cell) {  // integer cell coordinates of the child at its depth, 21 bits per axis
-                const uint64_t pc = cell[first + t];
-                const uint64_t cx = ((pc & 0x1FFFFFull) << 1) | (oct & 1u);
-                const uint64_t cy = (((pc >> 21) & 0x1FFFFFull) << 1) | ((oct >> 1) & 1u);
-                const uint64_t cz = (((pc >> 42) & 0x1FFFFFull) << 1) | ((oct >> 2) & 1u);
-                cell[c0 + k] = cx | (cy << 21) | (cz << 42);
-            }
-            mask |= 1u << oct;
-            ++k;
+__device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (ld_acquire_u32(bar) < target) {
         }
-        b = e;
+        __threadfence();
     }
-    nodes[first + t].child0 = c0;
-    nodes[first + t].meta = ((uint32_t)level << 8) | mask;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(LV_THREADS) octree_levels_kernel(Node* nodes, uint32_t* parent, uint64_t* cell, uint32_t cap_nodes,
+                                                                   const uint64_t* __restrict__ keys /* [n_words][m], sorted */,
+                                                                   int64_t m, int n_words, int key_depth, int max_pts, int max_depth,
+                                                                   uint64_t* status, LevelState* st) {
+    __shared__ uint32_t s_cnt[LV_TILE];  // children per node of the tile, then their exclusive prefix
+    __shared__ uint32_t s_wsum[LV_TILE / 32];
+    __shared__ uint32_t s_excl, s_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t oct = threadIdx.x & 7u, slot = threadIdx.x >> 3;
+    uint32_t first = 0, count = 1, epoch = 0;
+    for (int level = 0;; ++level) {
+        // the key word and the bit position of this level's octant
+        const int w = min(level / KEY_LEVELS, n_words - 1);
+        const int wl = min(KEY_LEVELS, key_depth - KEY_LEVELS * w);
+        const int shift = level < key_depth ? 3 * (wl - 1 - (level - KEY_LEVELS * w)) : 0;
+        const uint64_t* lk = keys + (size_t)w * m;
+        const uint32_t next_first = first + count;
+        const uint32_t n_tiles = (count + LV_TILE - 1) / LV_TILE;
+        const uint64_t tag = (uint64_t)(level + 1) << 34;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            uint32_t b[LV_ROUNDS], e[LV_ROUNDS], mask[LV_ROUNDS];
+#pragma unroll
+            for (int r = 0; r < LV_ROUNDS; ++r) {
+                const uint32_t t = tile * LV_TILE + r * 32 + slot;
+                uint32_t pt0 = 0, npts = 0;
+                if (t < count) {
+                    const uint4 tail = __ldcg(reinterpret_cast<const uint4*>(nodes + first + t) + 3);  // child0, pt0, npts, meta
+                    pt0 = tail.y;
+                    npts = tail.z;
+                }
+                bool split = t < count && !(npts <= (uint32_t)max_pts || level >= max_depth);  // octree.cpp:88
+                if (split && level >= key_depth) {  // its octant bits are not in the keys: the caller re-sorts
+                    if (oct == 0) {
+                        atomicOr(&st->level_flags[level], LV_FLAG_DEEPER);
+                        atomicOr(&st->flags, LV_FLAG_DEEPER);
+                    }
+                    split = false;
+                }
+                const uint32_t end = pt0 + npts;
+                uint32_t bb = 0;
+                if (split) bb = (oct == 0) ? pt0 : lower_bound_octant(lk, pt0, end, shift, oct);
+                const uint32_t next_b = __shfl_down_sync(0xffffffffu, bb, 1);
+                const uint32_t ee = (oct == 7) ? end : next_b;
+                const uint32_t any = __ballot_sync(0xffffffffu, split && ee > bb);
+                b[r] = bb;
+                e[r] = ee;
+                mask[r] = (any >> (lane & ~7)) & 0xFFu;
+                if (oct == 0) s_cnt[r * 32 + slot] = (uint32_t)__popc(mask[r]);
+            }
+            __syncthreads();
+            if (threadIdx.x < LV_TILE) {
+                const uint32_t v = s_cnt[threadIdx.x];
+                uint32_t incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                if (lane == 31) s_wsum[warp] = incl;
+                s_cnt[threadIdx.x] = incl - v;  // exclusive within the warp; the warps before it are added on use
+            }
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t total = 0;
+#pragma unroll
+                for (int k = 0; k < LV_TILE / 32; ++k) total += s_wsum[k];
+                if (lane == 0) st_relaxed_u64(status + tile, tag | ((tile == 0 ? 2ull : 1ull) << 32) | total);
+                uint32_t excl = 0;
+                if (tile > 0) {
+                    int64_t base = (int64_t)tile - 1;
+                    for (;;) {
+                        const int64_t j = base - lane;
+                        uint64_t v = tag | (2ull << 32);  // before tile 0: an empty inclusive prefix
+                        if (j >= 0) {
+                            do {
+                                v = ld_relaxed_u64(status + j);
+                            } while ((v >> 34) != (uint64_t)(level + 1) || ((v >> 32) & 3u) == 0);
+                        }
+                        const uint32_t incl_lanes = __ballot_sync(0xffffffffu, ((v >> 32) & 3u) == 2u);
+                        const int stop = incl_lanes ? __ffs(incl_lanes) - 1 : 31;
+                        uint32_t add = lane <= stop ? (uint32_t)v : 0u;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+                        excl += add;
+                        if (incl_lanes) break;
+                        base -= 32;
+                    }
+                    if (lane == 0) st_relaxed_u64(status + tile, tag | (2ull << 32) | (excl + total));
+                }
+                if (lane == 0) {
+                    s_excl = excl;
+                    s_total = total;
+                    if (tile == n_tiles - 1) st->level_total[level] = excl + total;
+                }
+            }
+            __syncthreads();
+            const uint32_t excl = s_excl;
+            const uint64_t want = (uint64_t)next_first + excl + s_total;
+            const bool fits = want <= cap_nodes;
+            if (threadIdx.x == 0) atomicMax(&st->needed, (uint32_t)min(want, (uint64_t)0xFFFFFFFFu));
+            if (!fits && threadIdx.x == 0) {
+                atomicOr(&st->level_flags[level], LV_FLAG_CAPACITY);
+                atomicOr(&st->flags, LV_FLAG_CAPACITY);
+            }
+            uint32_t leaves = 0;
+#pragma unroll
+            for (int r = 0; r < LV_ROUNDS; ++r) {
+                const uint32_t t = tile * LV_TILE + r * 32 + slot;
+                if (t >= count) continue;
+                Node* nd = nodes + first + t;
+                if (mask[r] == 0) {  // leaf: empty child mask
+                    if (oct == 0) {
+                        nd->child0 = 0;
+                        nd->meta = ((uint32_t)level << 8);
+                        ++leaves;
+                    }
+                    continue;
+                }
+                if (!fits) continue;
+                uint32_t off = s_cnt[r * 32 + slot];
+                for (int k = 0; k < r; ++k) off += s_wsum[k];
+                const uint32_t c0 = next_first + excl + off;
+                if (e[r] > b[r]) {
+                    const uint32_t k = (uint32_t)__popc(mask[r] & ((1u << oct) - 1u));
+                    const double2* box = reinterpret_cast<const double2*>(nd);
+                    const double2 q0 = __ldcg(box), q1 = __ldcg(box + 1), q2 = __ldcg(box + 2);
+                    const double lo[3] = {q0.x, q0.y, q1.x}, hi[3] = {q1.y, q2.x, q2.y};
+                    Node ch;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {  // octree.cpp:97-99, 115-120
+                        const double mid = dmul(dadd(lo[a], hi[a]), 0.5);
+                        const bool up = (oct >> a) & 1u;
+                        ch.lo[a] = up ? mid : lo[a];
+                        ch.hi[a] = up ? hi[a] : mid;
+                    }
+                    ch.child0 = 0;
+                    ch.pt0 = b[r];
+                    ch.npts = e[r] - b[r];
+                    ch.meta = ((uint32_t)(level + 1) << 8);
+                    nodes[c0 + k] = ch;
+                    parent[c0 + k] = first + t;
+                    if (cell) {  // integer cell coordinates of the child at its depth, 21 bits per axis
+                        const uint64_t pc = __ldcg(cell + first + t);
+                        const uint64_t cx = ((pc & 0x1FFFFFull) << 1) | (oct & 1u);
+                        const uint64_t cy = (((pc >> 21) & 0x1FFFFFull) << 1) | ((oct >> 1) & 1u);
+                        const uint64_t cz = (((pc >> 42) & 0x1FFFFFull) << 1) | ((oct >> 2) & 1u);
+                        cell[c0 + k] = cx | (cy << 21) | (cz << 42);
+                    }
+                }
+                if (oct == 0) {
+                    nd->child0 = c0;
+                    nd->meta = ((uint32_t)level << 8) | mask[r];
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) leaves += __shfl_xor_sync(0xffffffffu, leaves, o);
+            if (lane == 0 && leaves) atomicAdd(&st->n_leaves, leaves);
+            __syncthreads();  // s_cnt / s_wsum are reused by the next tile
+        }
+        grid_barrier(&st->barrier, gridDim.x * (++epoch));
+        const uint32_t total = ld_relaxed_u32(&st->level_total[level]);
+        const uint32_t flags = ld_relaxed_u32(&st->level_flags[level]);
+        if (flags != 0 || total == 0) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                st->depth = (uint32_t)level;
+                st->n_nodes = next_first;
+            }
+            break;
+        }
+        first = next_first;
+        count = total;
+    }
 }
 
 __global__ void root_node_kernel(Node* __restrict__ nodes, const double* __restrict__ root, uint32_t n) {
@@ -551,6 +716,7 @@ static void tree_reset(DeviceOctree& t) {
     keep.pts = t.pts; keep.cap_pts = t.cap_pts;
     keep.inv_perm = t.inv_perm; keep.cap_inv = t.cap_inv;
     keep.grid = t.grid; keep.cap_grid = t.cap_grid;
+    keep.full_keys = t.full_keys;
     t = keep;
 }
 
@@ -620,99 +786,127 @@ static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, i
         c->launches++;
     }
 
+    uint32_t* d_misc = nullptr;  // [0] pos_of_idx0
+    ICPB_TRY(devbuf_reserve(c, c->part_a, 4096));
+    d_misc = (uint32_t*)c->part_a.p;
+    LevelState* d_state = (LevelState*)(d_misc + 64);
+    LevelState h_state;
+    if (c->lv_grid == 0) {  // every block of the level kernel has to be resident
+        int per_sm = 0;
+        ICPB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, octree_levels_kernel, LV_THREADS, 0));
+        c->lv_grid = std::max(1, per_sm) * c->sm_count;
+    }
+
     // K1
     uint64_t *keys = nullptr, *keys_alt = nullptr;
     uint32_t *idx = nullptr, *idx_alt = nullptr;
     ICPB_TRY(devbuf_reserve(c, c->scratch1, (size_t)m * (2 * sizeof(uint64_t) + 2 * sizeof(uint32_t)) + 1024));
-    keys = (uint64_t*)c->scratch1.p;
-    keys_alt = keys + m;
-    idx = (uint32_t*)(keys_alt + m);
-    idx_alt = idx + m;
     const int kb = (int)((m + 255) / 256);
     const int n_words = std::max(1, (max_depth + KEY_LEVELS - 1) / KEY_LEVELS);
-    auto word_levels = [&](int w) { return std::min(KEY_LEVELS, max_depth - KEY_LEVELS * w); };
-    uint64_t* words_sorted = nullptr;  // deep trees: [n_words][m], sorted order
-    if (n_words == 1) {
-        morton_keys_kernel<<<kb, 256, 0, s>>>(d_xyz, m, d_root, max_depth, keys, idx);
-        c->launches++;
-        // K2
-        const int key_bits = 3 * max_depth;
-        if (key_bits > 0) ICPB_TRY(radix_sort_pairs(c, keys, keys_alt, idx, idx_alt, m, key_bits));
-    } else {
-        // deeper than one key word: least significant word first, each pass stable, the permutation carried along
-        ICPB_TRY(devbuf_reserve(c, c->scratch_keys, (size_t)m * sizeof(uint64_t) * 2 * n_words));
-        uint64_t* words = (uint64_t*)c->scratch_keys.p;  // [n_words][m], caller order
-        words_sorted = words + (size_t)n_words * m;
-        morton_keys_kernel<<<kb, 256, 0, s>>>(d_xyz, m, d_root, max_depth, words, idx);
-        c->launches++;
-        for (int w = n_words - 1; w >= 0; --w) {
-            gather_u64_kernel<<<kb, 256, 0, s>>>(words + (size_t)w * m, idx, m, keys);
-            c->launches++;
-            ICPB_TRY(radix_sort_pairs(c, keys, keys_alt, idx, idx_alt, m, 3 * word_levels(w)));
-        }
-        for (int w = 0; w < n_words; ++w) {
-            gather_u64_kernel<<<kb, 256, 0, s>>>(words + (size_t)w * m, idx, m, words_sorted + (size_t)w * m);
-            c->launches++;
-        }
-    }
-
-    // sorted points
-    if (t.cap_pts < m) {
-        if (t.pts) ICPB_CUDA(c, cudaFree(t.pts));
-        t.pts = nullptr;
-        t.cap_pts = 0;
-        ICPB_CUDA(c, cudaMalloc(&t.pts, (size_t)m * sizeof(TPoint)));
-        t.cap_pts = m;
-    }
-    uint32_t* d_misc = nullptr;  // [0] pos_of_idx0, [1] leaf counter, [2] scan total
-    ICPB_TRY(devbuf_reserve(c, c->part_a, 4096));
-    d_misc = (uint32_t*)c->part_a.p;
-    ICPB_CUDA(c, cudaMemsetAsync(d_misc, 0, 64, s));
-    gather_points_kernel<<<kb, 256, 0, s>>>(d_xyz, idx, m, t.pts, d_misc);
-    c->launches++;
-
-    // K3
-    ICPB_TRY(grow_nodes(c, t, std::max<int64_t>(m / 2, 1024)));
-    ICPB_CUDA(c, cudaMemsetAsync(t.parent, 0xFF, sizeof(uint32_t), s));
-    if (t.cell) ICPB_CUDA(c, cudaMemsetAsync(t.cell, 0, sizeof(uint64_t), s));
-    root_node_kernel<<<1, 32, 0, s>>>(t.nodes, d_root, (uint32_t)m);
-    c->launches++;
-    t.n_nodes = 1;
-    uint32_t first = 0, count = 1;
+    // Octant keys are taken (and sorted) only KEY_DEPTH_FIRST levels deep at first: real clouds stop splitting well above
+    // max_depth, the points of a leaf need no order among themselves (leaf scans break ties by original index), and every
+    // 8 key bits cost a pass over the points.  If some node still has to split below that depth the build starts over with
+    // keys of the full depth, and the tree remembers it for its next build.
+    int key_depth = (n_words == 1 && !t.full_keys) ? std::min(max_depth, KEY_DEPTH_FIRST) : max_depth;
     int level = 0;
-    uint32_t* counts = idx_alt;  // reuse: level sizes never exceed m
-    uint32_t* offs = (uint32_t*)keys_alt;
-    for (;; ++level) {
-        const int nb = (int)((count + 127) / 128);
-        // the key word and the bit position of this level's octant
-        const int w = std::min(level / KEY_LEVELS, n_words - 1);
-        const uint64_t* level_keys = words_sorted ? words_sorted + (size_t)w * m : keys;
-        const int shift = level < max_depth ? 3 * (word_levels(w) - 1 - (level - KEY_LEVELS * w)) : 0;
-        node_count_kernel<<<nb, 128, 0, s>>>(t.nodes, first, count, level_keys, level, max_pts, max_depth, shift, counts);
+    for (;;) {
+        keys = (uint64_t*)c->scratch1.p;
+        keys_alt = keys + m;
+        idx = (uint32_t*)(keys_alt + m);
+        idx_alt = idx + m;
+        auto word_levels = [&](int w) { return std::min(KEY_LEVELS, key_depth - KEY_LEVELS * w); };
+        uint64_t* words_sorted = nullptr;  // deep trees: [n_words][m], sorted order
+        if (n_words == 1) {
+            morton_keys_kernel<<<kb, 256, 0, s>>>(d_xyz, m, d_root, key_depth, keys, idx);
+            c->launches++;
+            // K2
+            ICPB_TRY(radix_sort_pairs(c, keys, keys_alt, idx, idx_alt, m, 3 * key_depth));
+        } else {
+            // deeper than one key word: least significant word first, each pass stable, the permutation carried along
+            ICPB_TRY(devbuf_reserve(c, c->scratch_keys, (size_t)m * sizeof(uint64_t) * 2 * n_words));
+            uint64_t* words = (uint64_t*)c->scratch_keys.p;  // [n_words][m], caller order
+            words_sorted = words + (size_t)n_words * m;
+            morton_keys_kernel<<<kb, 256, 0, s>>>(d_xyz, m, d_root, max_depth, words, idx);
+            c->launches++;
+            for (int w = n_words - 1; w >= 0; --w) {
+                gather_u64_kernel<<<kb, 256, 0, s>>>(words + (size_t)w * m, idx, m, keys);
+                c->launches++;
+                ICPB_TRY(radix_sort_pairs(c, keys, keys_alt, idx, idx_alt, m, 3 * word_levels(w)));
+            }
+            for (int w = 0; w < n_words; ++w) {
+                gather_u64_kernel<<<kb, 256, 0, s>>>(words + (size_t)w * m, idx, m, words_sorted + (size_t)w * m);
+                c->launches++;
+            }
+        }
+
+        // sorted points
+        if (t.cap_pts < m) {
+            if (t.pts) ICPB_CUDA(c, cudaFree(t.pts));
+            t.pts = nullptr;
+            t.cap_pts = 0;
+            ICPB_CUDA(c, cudaMalloc(&t.pts, (size_t)m * sizeof(TPoint)));
+            t.cap_pts = m;
+        }
+        ICPB_CUDA(c, cudaMemsetAsync(d_misc, 0, 64, s));
+        gather_points_kernel<<<kb, 256, 0, s>>>(d_xyz, idx, m, t.pts, d_misc);
         c->launches++;
-        ICPB_TRY(exclusive_scan_u32(c, counts, offs, count, d_misc + 2));
-        uint32_t n_children = 0;
-        ICPB_CUDA(c, cudaMemcpyAsync(&n_children, d_misc + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        ICPB_CUDA(c, cudaStreamSynchronize(s));
-        const uint32_t next_first = first + count;
-        ICPB_TRY(grow_nodes(c, t, (int64_t)next_first + n_children));
-        node_emit_kernel<<<nb, 128, 0, s>>>(t.nodes, first, count, level_keys, level, max_pts, max_depth, shift, offs, next_first,
-                                            d_misc + 1, t.parent, t.cell);
+
+        // K3
+        ICPB_TRY(grow_nodes(c, t, std::max<int64_t>(m / 2, 1024)));
+        ICPB_CUDA(c, cudaMemsetAsync(t.parent, 0xFF, sizeof(uint32_t), s));
+        if (t.cell) ICPB_CUDA(c, cudaMemsetAsync(t.cell, 0, sizeof(uint64_t), s));
+        root_node_kernel<<<1, 32, 0, s>>>(t.nodes, d_root, (uint32_t)m);
         c->launches++;
-        t.n_nodes = (int64_t)next_first + n_children;
-        if (n_children == 0) break;
-        first = next_first;
-        count = n_children;
+        t.n_nodes = 1;
+        // the level loop, on the device.  A node table that turns out too small is grown and the levels run again.
+        const uint64_t* level_keys = words_sorted ? words_sorted : keys;
+        const size_t status_bytes = ((size_t)m / LV_TILE + 2) * sizeof(uint64_t);  // one word per tile of a level
+        ICPB_TRY(devbuf_reserve(c, c->scratch3, status_bytes));
+        uint64_t* status = (uint64_t*)c->scratch3.p;
+        bool deeper_keys = false;
+        for (;;) {
+            ICPB_CUDA(c, cudaMemsetAsync(d_state, 0, sizeof(LevelState), s));
+            ICPB_CUDA(c, cudaMemsetAsync(status, 0, status_bytes, s));
+            Node* a_nodes = t.nodes;
+            uint32_t* a_parent = t.parent;
+            uint64_t* a_cell = t.cell;
+            uint32_t a_cap = (uint32_t)std::min<int64_t>(t.cap_nodes, 0xFFFFFFFFll);
+            int64_t a_m = m;
+            int a_words = n_words, a_kd = key_depth, a_maxpts = max_pts, a_maxdepth = max_depth;
+            void* args[] = {&a_nodes, &a_parent, &a_cell, &a_cap, &level_keys, &a_m, &a_words, &a_kd, &a_maxpts, &a_maxdepth, &status, &d_state};
+            ICPB_CUDA(c, cudaLaunchCooperativeKernel((const void*)octree_levels_kernel, dim3(c->lv_grid), dim3(LV_THREADS), args, 0, s));
+            c->launches++;
+            ICPB_CUDA(c, cudaMemcpyAsync(&h_state, d_state, sizeof(LevelState), cudaMemcpyDeviceToHost, s));
+            ICPB_CUDA(c, cudaStreamSynchronize(s));
+            if (h_state.flags & LV_FLAG_DEEPER) {
+                deeper_keys = true;
+                break;
+            }
+            if (!(h_state.flags & LV_FLAG_CAPACITY)) break;
+            if (t.cap_nodes >= 0xFFFFFFFFll) {
+                c->err = "octree: more than 2^32 nodes";
+                return ICP_INVALID_ARGUMENT;
+            }
+            ICPB_TRY(grow_nodes(c, t, std::max<int64_t>((int64_t)h_state.needed, t.cap_nodes * 2)));
+            ICPB_CUDA(c, cudaMemsetAsync(t.parent, 0xFF, sizeof(uint32_t), s));
+            if (t.cell) ICPB_CUDA(c, cudaMemsetAsync(t.cell, 0, sizeof(uint64_t), s));
+            root_node_kernel<<<1, 32, 0, s>>>(t.nodes, d_root, (uint32_t)m);
+        }
+        level = (int)h_state.depth;
+        t.n_nodes = h_state.n_nodes;
+        if (!deeper_keys) break;
+        t.full_keys = true;
+        key_depth = max_depth;
     }
     t.depth = level;
-    uint32_t misc[2];
+    uint32_t misc[1];
     double root[6];
     ICPB_CUDA(c, cudaMemcpyAsync(misc, d_misc, sizeof misc, cudaMemcpyDeviceToHost, s));
     ICPB_CUDA(c, cudaMemcpyAsync(root, d_root, sizeof root, cudaMemcpyDeviceToHost, s));
     ICPB_CUDA(c, cudaStreamSynchronize(s));
     ICPB_CUDA(c, cudaGetLastError());
     t.pos_of_idx0 = misc[0];
-    t.n_leaves = misc[1];
+    t.n_leaves = h_state.n_leaves;
     for (int a = 0; a < 3; ++a) {
         t.root_lo[a] = root[a];
         t.root_hi[a] = root[3 + a];

@@ -15,6 +15,7 @@ struct DeviceOctree {
     uint32_t* parent = nullptr;  // parent node index per node (root: 0xFFFFFFFF)
     int64_t n_nodes = 0, cap_nodes = 0, cap_cell = 0, cap_pts = 0, cap_inv = 0, cap_grid = 0;
     bool inv_valid = false;
+    bool full_keys = false;  // an earlier build of this tree needed octant keys down to max_depth (build_tree)
     TPoint* pts = nullptr;  // Morton-sorted target points (xyz + original index)
     int64_t n_pts = 0;
     int64_t n_leaves = 0;
@@ -134,6 +135,7 @@ struct Ctx {
     bool p2p = false;
     size_t nn_smem_opt_in = 0;    // nn_kernel's dynamic shared memory opt-in done up to this size (deep octrees)
     bool rs_smem_opt_in = false;  // radix_scatter_kernel's dynamic shared memory opt-in done for this handle's device
+    int lv_grid = 0;              // blocks of the cooperative octree level kernel (all resident)
     unsigned int mail_epoch = 0;
     unsigned int mail_run = 0;       // sharded runs started on this handle (the same number on every rank): high part of the epoch
     unsigned long long* d_counters = nullptr;  // see NNArgs::counters (4 entries)
@@ -204,7 +206,6 @@ int sort_pairs_u64_u32(Ctx* c, uint64_t*& keys, uint64_t*& keys_alt, uint32_t*& 
 // build.cu
 int octree_build_device(Ctx* c, const double* d_tgt_xyz, int64_t m, int max_pts, int max_depth);
 void octree_free(Ctx* c);
-int exclusive_scan_u32(Ctx* c, const uint32_t* d_in, uint32_t* d_out, int64_t n, uint32_t* d_total);
 // Morton-orders n query points (AoS, device) for traversal coherence: fills SoA coordinates and the
 // permutation (internal slot -> original index).
 int order_queries(Ctx* c, const double* d_q_xyz, int64_t n, double* sx, double* sy, double* sz, uint32_t* perm);
