@@ -473,13 +473,14 @@ __device__ __forceinline__ uint32_t lower_bound_octant(const uint64_t* __restric
     return lo;
 }
 
-// All levels in ONE cooperative launch (every block resident, a grid barrier between levels).  Eight lanes per node: lane
-// `oct` finds where octant `oct` starts in the node's sorted range, its neighbour's start is where it ends.  A block takes
-// tiles of LV_TILE nodes of the level in increasing order; the first-child index of a node is the number of children of all
-// nodes before it, found without a second pass: a tile publishes its own child count at once and looks back over the
-// earlier tiles' words (chained scan, as in the sort above; a block never waits for a later tile, so it cannot deadlock).
-// The node numbering is the breadth-first one a count / scan / emit sequence per level gives.
-constexpr int LV_THREADS = 256, LV_ROUNDS = 4, LV_TILE = 32 * LV_ROUNDS;
+// All levels in ONE cooperative launch (every block resident, a grid barrier between levels).  A block takes tiles of
+// LV_TILE nodes of the level in increasing order.  One thread per node first sorts out the leaves (most nodes of the deep
+// levels) and lists the nodes that split, in order.  Eight lanes per listed node then find its children: lane `oct` looks up
+// where octant `oct` starts in the node's sorted range, its neighbour's start is where it ends.  The first-child index of a
+// node is the number of children of all nodes before it, found without a second pass: a tile publishes its own child count
+// at once and looks back over the earlier tiles' words (chained scan, as in the sort above; a block never waits for a later
+// tile, so it cannot deadlock).  The node numbering is the breadth-first one a count / scan / emit sequence per level gives.
+constexpr int LV_THREADS = 256, LV_ROUNDS = 2, LV_TILE = LV_THREADS * LV_ROUNDS, LV_WARPS = LV_THREADS / 32, LV_UNROLL = 4;
 constexpr uint32_t LV_FLAG_CAPACITY = 1, LV_FLAG_DEEPER = 2;
 
 struct LevelState {  // zeroed before the launch
@@ -491,6 +492,10 @@ struct LevelState {  // zeroed before the launch
     uint32_t needed;           // node slots wanted so far
     uint32_t depth, n_nodes;   // the result
     uint32_t barrier;
+#ifdef ICPB_LVTIME
+    unsigned long long t_level[68];  // profiling build: globaltimer when block 0 left each level's barrier
+    uint32_t n_level[68];
+#endif
 };
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
@@ -520,11 +525,21 @@ __global__ void __launch_bounds__(LV_THREADS) octree_levels_kernel(Node* nodes, 
                                                                    const uint64_t* __restrict__ keys /* [n_words][m], sorted */,
                                                                    int64_t m, int n_words, int key_depth, int max_pts, int max_depth,
                                                                    uint64_t* status, LevelState* st) {
-    __shared__ uint32_t s_cnt[LV_TILE];  // children per node of the tile, then their exclusive prefix
-    __shared__ uint32_t s_wsum[LV_TILE / 32];
+    __shared__ uint32_t s_list[LV_TILE];      // the tile's nodes that split (index within the level), in order
+    __shared__ uint32_t s_cnt[LV_TILE];       // children per listed node, then their exclusive prefix
+    __shared__ uint32_t s_b[LV_TILE * 8];     // where octant o of listed node g starts: s_b[g * 8 + o]
+    __shared__ uint32_t s_w[LV_WARPS];
     __shared__ uint32_t s_excl, s_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t oct = threadIdx.x & 7u, slot = threadIdx.x >> 3;
+    const uint32_t oct = threadIdx.x & 7u, group = threadIdx.x >> 3;
+    const uint32_t lt = (1u << lane) - 1u;
+#ifdef ICPB_LVTIME
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        st->t_level[0] = t0;
+    }
+#endif
     uint32_t first = 0, count = 1, epoch = 0;
     for (int level = 0;; ++level) {
         // the key word and the bit position of this level's octant
@@ -533,55 +548,127 @@ __global__ void __launch_bounds__(LV_THREADS) octree_levels_kernel(Node* nodes, 
         const int shift = level < key_depth ? 3 * (wl - 1 - (level - KEY_LEVELS * w)) : 0;
         const uint64_t* lk = keys + (size_t)w * m;
         const uint32_t next_first = first + count;
-        const uint32_t n_tiles = (count + LV_TILE - 1) / LV_TILE;
+        // tile size of this level: LV_TILE nodes, less when the level has too few nodes to give every block one (the upper
+        // levels: every node splits, and its searches run over long ranges -- spread them over the blocks)
+        const uint32_t tn = min((uint32_t)LV_TILE, max(32u, ((count + gridDim.x - 1) / gridDim.x + 31u) & ~31u));
+        const uint32_t n_tiles = (count + tn - 1) / tn;
         const uint64_t tag = (uint64_t)(level + 1) << 34;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            uint32_t b[LV_ROUNDS], e[LV_ROUNDS], mask[LV_ROUNDS];
+            // ---- one thread per node: leaves are finished here, the nodes that split are listed in order ----
+            uint32_t n_split = 0, leaves = 0;
 #pragma unroll
             for (int r = 0; r < LV_ROUNDS; ++r) {
-                const uint32_t t = tile * LV_TILE + r * 32 + slot;
-                uint32_t pt0 = 0, npts = 0;
-                if (t < count) {
-                    const uint4 tail = __ldcg(reinterpret_cast<const uint4*>(nodes + first + t) + 3);  // child0, pt0, npts, meta
-                    pt0 = tail.y;
-                    npts = tail.z;
-                }
-                bool split = t < count && !(npts <= (uint32_t)max_pts || level >= max_depth);  // octree.cpp:88
-                if (split && level >= key_depth) {  // its octant bits are not in the keys: the caller re-sorts
-                    if (oct == 0) {
+                const uint32_t in_tile = r * LV_THREADS + threadIdx.x;
+                const uint32_t t = tile * tn + in_tile;
+                bool split = false;
+                if (in_tile < tn && t < count) {
+                    Node* nd = nodes + first + t;
+                    const uint4 tail = __ldcg(reinterpret_cast<const uint4*>(nd) + 3);  // child0, pt0, npts, meta
+                    split = !(tail.z <= (uint32_t)max_pts || level >= max_depth);       // octree.cpp:88
+                    if (split && level >= key_depth) {  // its octant bits are not in the keys: the caller re-sorts
                         atomicOr(&st->level_flags[level], LV_FLAG_DEEPER);
                         atomicOr(&st->flags, LV_FLAG_DEEPER);
+                        split = false;
                     }
-                    split = false;
+                    if (!split) {  // leaf: empty child mask
+                        nd->child0 = 0;
+                        nd->meta = ((uint32_t)level << 8);
+                        ++leaves;
+                    }
                 }
-                const uint32_t end = pt0 + npts;
-                uint32_t bb = 0;
-                if (split) bb = (oct == 0) ? pt0 : lower_bound_octant(lk, pt0, end, shift, oct);
-                const uint32_t next_b = __shfl_down_sync(0xffffffffu, bb, 1);
-                const uint32_t ee = (oct == 7) ? end : next_b;
-                const uint32_t any = __ballot_sync(0xffffffffu, split && ee > bb);
-                b[r] = bb;
-                e[r] = ee;
-                mask[r] = (any >> (lane & ~7)) & 0xFFu;
-                if (oct == 0) s_cnt[r * 32 + slot] = (uint32_t)__popc(mask[r]);
+                const uint32_t mine = __ballot_sync(0xffffffffu, split);
+                if (lane == 0) s_w[warp] = (uint32_t)__popc(mine);
+                __syncthreads();
+                uint32_t before = n_split, all = 0;
+#pragma unroll
+                for (int k = 0; k < LV_WARPS; ++k) {
+                    const uint32_t v = s_w[k];
+                    if (k < warp) before += v;
+                    all += v;
+                }
+                if (split) s_list[before + __popc(mine & lt)] = t;
+                n_split += all;
+                __syncthreads();
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) leaves += __shfl_xor_sync(0xffffffffu, leaves, o);
+            if (lane == 0 && leaves) atomicAdd(&st->n_leaves, leaves);
+
+            // ---- eight lanes per listed node: octant starts, child count ----
+            for (uint32_t g0 = 0; g0 < n_split; g0 += LV_UNROLL * (LV_THREADS / 8)) {
+                uint32_t bb[LV_UNROLL], hi[LV_UNROLL], end[LV_UNROLL];
+#pragma unroll
+                for (int u = 0; u < LV_UNROLL; ++u) {
+                    const uint32_t g = g0 + u * (LV_THREADS / 8) + group;
+                    bb[u] = hi[u] = end[u] = 0;
+                    if (g < n_split) {
+                        const uint4 tail = __ldcg(reinterpret_cast<const uint4*>(nodes + first + s_list[g]) + 3);
+                        end[u] = tail.y + tail.z;
+                        bb[u] = tail.y;
+                        hi[u] = (oct == 0) ? tail.y : end[u];
+                    }
+                }
+                // LV_UNROLL searches side by side (independent loads in flight): first position in [bb, hi) whose octant
+                // at `shift` is >= oct
+                for (bool more = true; more;) {
+                    more = false;
+#pragma unroll
+                    for (int u = 0; u < LV_UNROLL; ++u) {
+                        if (bb[u] < hi[u]) {
+                            const uint32_t mid = bb[u] + ((hi[u] - bb[u]) >> 1);
+                            const uint32_t o = (uint32_t)((lk[mid] >> shift) & 7u);
+                            if (o < oct) bb[u] = mid + 1; else hi[u] = mid;
+                            more = true;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < LV_UNROLL; ++u) {
+                    const uint32_t g = g0 + u * (LV_THREADS / 8) + group;
+                    if (g < n_split) s_b[g * 8 + oct] = bb[u];
+                    const uint32_t next_b = __shfl_down_sync(0xffffffffu, bb[u], 1);
+                    const uint32_t ee = (oct == 7) ? end[u] : next_b;
+                    const uint32_t any = __ballot_sync(0xffffffffu, g < n_split && ee > bb[u]);
+                    if (g < n_split && oct == 0) s_cnt[g] = (uint32_t)__popc((any >> (lane & ~7)) & 0xFFu);
+                }
             }
             __syncthreads();
-            if (threadIdx.x < LV_TILE) {
-                const uint32_t v = s_cnt[threadIdx.x];
-                uint32_t incl = v;
+
+            // ---- exclusive prefix of the child counts over the list; the tile's total ----
+            uint32_t total = 0;
+            {
+                uint32_t v[LV_ROUNDS], sum = 0;
+#pragma unroll
+                for (int k = 0; k < LV_ROUNDS; ++k) {
+                    const uint32_t g = threadIdx.x * LV_ROUNDS + k;
+                    v[k] = g < n_split ? s_cnt[g] : 0u;
+                    sum += v[k];
+                }
+                uint32_t incl = sum;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
                     if (lane >= o) incl += u;
                 }
-                if (lane == 31) s_wsum[warp] = incl;
-                s_cnt[threadIdx.x] = incl - v;  // exclusive within the warp; the warps before it are added on use
-            }
-            __syncthreads();
-            if (warp == 0) {
-                uint32_t total = 0;
+                if (lane == 31) s_w[warp] = incl;
+                __syncthreads();
+                uint32_t run = incl - sum;
 #pragma unroll
-                for (int k = 0; k < LV_TILE / 32; ++k) total += s_wsum[k];
+                for (int k = 0; k < LV_WARPS; ++k) {
+                    const uint32_t u = s_w[k];
+                    if (k < warp) run += u;
+                    total += u;
+                }
+#pragma unroll
+                for (int k = 0; k < LV_ROUNDS; ++k) {
+                    const uint32_t g = threadIdx.x * LV_ROUNDS + k;
+                    if (g < n_split) s_cnt[g] = run;
+                    run += v[k];
+                }
+            }
+
+            // ---- children of all tiles before this one (warp 0 looks back, 32 tiles at a time) ----
+            if (warp == 0) {
                 if (lane == 0) st_relaxed_u64(status + tile, tag | ((tile == 0 ? 2ull : 1ull) << 32) | total);
                 uint32_t excl = 0;
                 if (tile > 0) {
@@ -615,67 +702,75 @@ __global__ void __launch_bounds__(LV_THREADS) octree_levels_kernel(Node* nodes, 
             const uint32_t excl = s_excl;
             const uint64_t want = (uint64_t)next_first + excl + s_total;
             const bool fits = want <= cap_nodes;
-            if (threadIdx.x == 0) atomicMax(&st->needed, (uint32_t)min(want, (uint64_t)0xFFFFFFFFu));
-            if (!fits && threadIdx.x == 0) {
-                atomicOr(&st->level_flags[level], LV_FLAG_CAPACITY);
-                atomicOr(&st->flags, LV_FLAG_CAPACITY);
+            if (threadIdx.x == 0) {
+                atomicMax(&st->needed, (uint32_t)min(want, (uint64_t)0xFFFFFFFFu));
+                if (!fits) {
+                    atomicOr(&st->level_flags[level], LV_FLAG_CAPACITY);
+                    atomicOr(&st->flags, LV_FLAG_CAPACITY);
+                }
             }
-            uint32_t leaves = 0;
+
+            // ---- eight lanes per listed node: the children ----
+            if (fits) {
+                for (uint32_t g0 = 0; g0 < n_split; g0 += LV_THREADS / 8) {  // (same trip count for every lane: ballot inside)
+                    const uint32_t g = g0 + group;
+                    const bool have = g < n_split;
+                    const uint32_t t = have ? s_list[g] : 0u;
+                    Node* nd = nodes + first + t;
+                    uint32_t bb = 0, ee = 0;
+                    if (have) {
+                        const uint4 tail = __ldcg(reinterpret_cast<const uint4*>(nd) + 3);
+                        bb = s_b[g * 8 + oct];
+                        ee = (oct == 7) ? tail.y + tail.z : s_b[g * 8 + oct + 1];
+                    }
+                    const uint32_t any = __ballot_sync(0xffffffffu, ee > bb);
+                    if (!have) continue;
+                    const uint32_t mask = (any >> (lane & ~7)) & 0xFFu;
+                    const uint32_t c0 = next_first + excl + s_cnt[g];
+                    if (ee > bb) {
+                        const uint32_t k = (uint32_t)__popc(mask & ((1u << oct) - 1u));
+                        const double2* box = reinterpret_cast<const double2*>(nd);
+                        const double2 q0 = __ldcg(box), q1 = __ldcg(box + 1), q2 = __ldcg(box + 2);
+                        const double lo[3] = {q0.x, q0.y, q1.x}, hi[3] = {q1.y, q2.x, q2.y};
+                        Node ch;
 #pragma unroll
-            for (int r = 0; r < LV_ROUNDS; ++r) {
-                const uint32_t t = tile * LV_TILE + r * 32 + slot;
-                if (t >= count) continue;
-                Node* nd = nodes + first + t;
-                if (mask[r] == 0) {  // leaf: empty child mask
+                        for (int a = 0; a < 3; ++a) {  // octree.cpp:97-99, 115-120
+                            const double mid = dmul(dadd(lo[a], hi[a]), 0.5);
+                            const bool up = (oct >> a) & 1u;
+                            ch.lo[a] = up ? mid : lo[a];
+                            ch.hi[a] = up ? hi[a] : mid;
+                        }
+                        ch.child0 = 0;
+                        ch.pt0 = bb;
+                        ch.npts = ee - bb;
+                        ch.meta = ((uint32_t)(level + 1) << 8);
+                        nodes[c0 + k] = ch;
+                        parent[c0 + k] = first + t;
+                        if (cell) {  // integer cell coordinates of the child at its depth, 21 bits per axis
+                            const uint64_t pc = __ldcg(cell + first + t);
+                            const uint64_t cx = ((pc & 0x1FFFFFull) << 1) | (oct & 1u);
+                            const uint64_t cy = (((pc >> 21) & 0x1FFFFFull) << 1) | ((oct >> 1) & 1u);
+                            const uint64_t cz = (((pc >> 42) & 0x1FFFFFull) << 1) | ((oct >> 2) & 1u);
+                            cell[c0 + k] = cx | (cy << 21) | (cz << 42);
+                        }
+                    }
                     if (oct == 0) {
-                        nd->child0 = 0;
-                        nd->meta = ((uint32_t)level << 8);
-                        ++leaves;
+                        nd->child0 = c0;
+                        nd->meta = ((uint32_t)level << 8) | mask;
                     }
-                    continue;
-                }
-                if (!fits) continue;
-                uint32_t off = s_cnt[r * 32 + slot];
-                for (int k = 0; k < r; ++k) off += s_wsum[k];
-                const uint32_t c0 = next_first + excl + off;
-                if (e[r] > b[r]) {
-                    const uint32_t k = (uint32_t)__popc(mask[r] & ((1u << oct) - 1u));
-                    const double2* box = reinterpret_cast<const double2*>(nd);
-                    const double2 q0 = __ldcg(box), q1 = __ldcg(box + 1), q2 = __ldcg(box + 2);
-                    const double lo[3] = {q0.x, q0.y, q1.x}, hi[3] = {q1.y, q2.x, q2.y};
-                    Node ch;
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {  // octree.cpp:97-99, 115-120
-                        const double mid = dmul(dadd(lo[a], hi[a]), 0.5);
-                        const bool up = (oct >> a) & 1u;
-                        ch.lo[a] = up ? mid : lo[a];
-                        ch.hi[a] = up ? hi[a] : mid;
-                    }
-                    ch.child0 = 0;
-                    ch.pt0 = b[r];
-                    ch.npts = e[r] - b[r];
-                    ch.meta = ((uint32_t)(level + 1) << 8);
-                    nodes[c0 + k] = ch;
-                    parent[c0 + k] = first + t;
-                    if (cell) {  // integer cell coordinates of the child at its depth, 21 bits per axis
-                        const uint64_t pc = __ldcg(cell + first + t);
-                        const uint64_t cx = ((pc & 0x1FFFFFull) << 1) | (oct & 1u);
-                        const uint64_t cy = (((pc >> 21) & 0x1FFFFFull) << 1) | ((oct >> 1) & 1u);
-                        const uint64_t cz = (((pc >> 42) & 0x1FFFFFull) << 1) | ((oct >> 2) & 1u);
-                        cell[c0 + k] = cx | (cy << 21) | (cz << 42);
-                    }
-                }
-                if (oct == 0) {
-                    nd->child0 = c0;
-                    nd->meta = ((uint32_t)level << 8) | mask[r];
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) leaves += __shfl_xor_sync(0xffffffffu, leaves, o);
-            if (lane == 0 && leaves) atomicAdd(&st->n_leaves, leaves);
-            __syncthreads();  // s_cnt / s_wsum are reused by the next tile
+            __syncthreads();  // the shared lists are reused by the next tile
         }
         grid_barrier(&st->barrier, gridDim.x * (++epoch));
+#ifdef ICPB_LVTIME
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            st->t_level[level + 1] = t1;
+            st->n_level[level] = count;
+        }
+#endif
         const uint32_t total = ld_relaxed_u32(&st->level_total[level]);
         const uint32_t flags = ld_relaxed_u32(&st->level_flags[level]);
         if (flags != 0 || total == 0) {
@@ -860,7 +955,7 @@ static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, i
         t.n_nodes = 1;
         // the level loop, on the device.  A node table that turns out too small is grown and the levels run again.
         const uint64_t* level_keys = words_sorted ? words_sorted : keys;
-        const size_t status_bytes = ((size_t)m / LV_TILE + 2) * sizeof(uint64_t);  // one word per tile of a level
+        const size_t status_bytes = ((size_t)m / LV_TILE + (size_t)c->lv_grid + 2) * sizeof(uint64_t);  // one word per tile of a level
         ICPB_TRY(devbuf_reserve(c, c->scratch3, status_bytes));
         uint64_t* status = (uint64_t*)c->scratch3.p;
         bool deeper_keys = false;
@@ -894,6 +989,10 @@ static int build_tree(Ctx* c, DeviceOctree& t, const double* d_xyz, int64_t m, i
         }
         level = (int)h_state.depth;
         t.n_nodes = h_state.n_nodes;
+#ifdef ICPB_LVTIME
+        for (int l = 0; l <= level; ++l)
+            fprintf(stderr, "[icp_b200] level %2d: %8u nodes %8.1f us\n", l, h_state.n_level[l], (double)(h_state.t_level[l + 1] - h_state.t_level[l]) / 1000.0);
+#endif
         if (!deeper_keys) break;
         t.full_keys = true;
         key_depth = max_depth;
