@@ -196,7 +196,10 @@ __global__ void __launch_bounds__(256) morton_keys_kernel(const double* __restri
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ROUNDS = 16;                            // elements per thread
+#ifndef ICPB_RS_ROUNDS
+#define ICPB_RS_ROUNDS 16
+#endif
+constexpr int RS_ROUNDS = ICPB_RS_ROUNDS;                            // elements per thread
 constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;          // 4096 elements per block
 constexpr int RS_CHUNK = 32 * RS_ROUNDS;                 // per warp
 
@@ -313,6 +316,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_onesweep_kernel(const uin
         }
     }
     __syncthreads();
+    uint32_t my_cnt = 0;
     {
         // thread d: this tile's count of digit d; publish it; scan over the digits (staging order) and per-warp offsets
         const int d = threadIdx.x;
@@ -339,7 +343,27 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_onesweep_kernel(const uin
             wh[w][d] = run;
             run += c;
         }
-        // look back over the tiles before this one
+        my_cnt = cnt;
+    }
+    __syncthreads();
+    {
+        const uint32_t* off = wh[warp];
+#pragma unroll
+        for (int r = 0; r < RS_ROUNDS; ++r) {
+            const int64_t i = chunk_base + (int64_t)r * 32 + lane;
+            if (i < n) {
+                const uint32_t d = (uint32_t)((key[r] >> shift) & 0xFF);
+                const uint32_t dst = off[d] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xFFFFu);  // position inside the staged tile
+                skeys[dst] = key[r];
+                svals[dst] = vals_in[i];
+            }
+        }
+    }
+    {
+        // look back over the tiles before this one (after the staging: the predecessors had that long to publish their prefixes)
+        const int d = threadIdx.x;
+        const uint32_t cnt = my_cnt;
+        uint64_t* my = status + (size_t)tile * 256 + d;
         uint64_t excl = 0;
         if (tile > 0) {
             const uint64_t* look = my - 256;
@@ -355,20 +379,6 @@ __global__ void __launch_bounds__(RS_THREADS, 3) radix_onesweep_kernel(const uin
             st_relaxed_u64(my, (excl + cnt) | OS_INCL);
         }
         gbase[d] = gstart[d] + (uint32_t)excl;
-    }
-    __syncthreads();
-    {
-        const uint32_t* off = wh[warp];
-#pragma unroll
-        for (int r = 0; r < RS_ROUNDS; ++r) {
-            const int64_t i = chunk_base + (int64_t)r * 32 + lane;
-            if (i < n) {
-                const uint32_t d = (uint32_t)((key[r] >> shift) & 0xFF);
-                const uint32_t dst = off[d] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xFFFFu);  // position inside the staged tile
-                skeys[dst] = key[r];
-                svals[dst] = vals_in[i];
-            }
-        }
     }
     __syncthreads();
     const int count = (int)min((int64_t)RS_TILE, n - block_base);
