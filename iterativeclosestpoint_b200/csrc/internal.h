@@ -90,7 +90,7 @@ struct Ctx {
     int opt_grid_levels = 3;         // pyramid height (base level + finer ones)
     int opt_grid_coarse = 1;         // levels coarser than the base one (balanced walk only: balls wider than a base cell)
     double opt_base_occupancy = 4.0; // mean points per occupied cell the base level must still have
-    int opt_range_max = 64;          // inner cells up to this many points are entered as plain point ranges
+    int opt_range_max = 96;          // inner cells up to this many points are entered as plain point ranges (swept: tools/opt_sweep.py)
     int opt_walk_bias = -100;        // cell walk: levels finer (+) or coarser (-) than 'cell >= ball box'; -100 = per mode
                                      // (measured best: -2 for the per-thread walk, 0 for the balanced one)
     int opt_walk_max_cells = 27;     // cell walk gives way to the climbing search beyond this many cells
