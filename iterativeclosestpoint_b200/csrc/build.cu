@@ -4,9 +4,10 @@
 //   K0  bbox        strict min/max of the target + the 0.001 expansion            (octree.cpp:47-64)
 //   K1  keys        per point, the octant path of buildTree's recursion, obtained by the SAME FP64
 //                   bisection mid = (lo+hi)/2, bit = p > mid, 3 bits per level      (octree.cpp:97-110)
-//   K2  sort        stable LSD radix sort of (key, index), 8 bits per pass
-//   K3  nodes       level-by-level emission of the node table: a prefix with more than max_pts points and
-//                   depth < max_depth is an inner node, otherwise a leaf            (octree.cpp:88)
+//   K2  sort        stable LSD radix sort of (key, index), 8 bits per pass, one kernel per pass (chained scan); the keys are
+//                   taken 16 levels deep first and to the full depth only if some node has to split below that
+//   K3  nodes       all levels in one cooperative launch: a prefix with more than max_pts points and depth < max_depth is an
+//                   inner node, otherwise a leaf (octree.cpp:88); breadth-first numbering
 //
 // Cell membership is decided by comparisons against bisection midpoints, never by scaling, so every
 // point lands in exactly the reference's leaf and every box is bit-identical to the reference's.
