@@ -199,7 +199,8 @@ int icp_comm_destroy(icp_handle h);
  * points by region over NVLink (a range of the caller's order says nothing about where its points are); the moved points
  * travel home before the write-back, so the caller gets ITS shard back in ITS order.  A stop flag raised on any rank ends
  * the run on every rank in the same iteration (ICP_CANCELLED, sources untouched).  icp_source_upload /
- * icp_register_resident on a handle with a communicator behave the same way. */
+ * icp_register_resident on a handle with a communicator behave the same way.  A rank's shard may be EMPTY (n_shard = 0, the
+ * pointer may then be NULL): the rank still takes part in every collective and returns the common result. */
 int icp_register_sharded(icp_handle h, double* src_shard_xyz, int64_t n_shard, int64_t n_src_global,
                          const double* tgt_xyz, int64_t n_tgt, icp_result* out, const volatile int* stop_flag);
 
