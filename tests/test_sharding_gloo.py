@@ -77,6 +77,20 @@ def test_rank_ordered_merge_matches_whole_cloud_statistics():
         assert abs(m[1] - whole[1]) <= 1e-14 * whole[1] and abs(m[2] - whole[2]) <= 1e-12 * whole[2]
 
 
+def test_rank_ordered_merge_with_more_ranks_than_points():
+    """A world larger than the cloud leaves ranks with EMPTY shards (their partial has n = 0); the merge in rank order must
+    still give the whole cloud's statistics (the device path: tools/sharded_check.py with ICP_CHECK_SRC, profiles/r2_sharded_check_8gpu_21pts.json)."""
+    d = np.array([0.3, 0.1, 0.25, 0.7, 0.05])
+    whole = shard_merge.stat_partial(d)
+    for world in (8, 16):
+        cuts = [sharding.shard_range(len(d), k, world) for k in range(world)]
+        assert sum(1 for a, b in cuts if a == b) == world - len(d)
+        parts = [shard_merge.stat_partial(d[a:b]) for a, b in cuts]
+        m = shard_merge.merge_in_rank_order(parts)
+        assert m[0] == whole[0] and m[3] == whole[3] and m[4] == whole[4]
+        assert abs(m[1] - whole[1]) <= 1e-15 and abs(m[2] - whole[2]) <= 1e-15
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
